@@ -1,0 +1,164 @@
+// Pasta field arithmetic for sm_100a: 8x32-bit limbs, Montgomery form (R = 2^256), values always in [0, m).
+// Memory format is 4x u64 little-endian = the same 32 bytes Rust's `Fp([u64;4])` holds, so a warp reading 32
+// consecutive elements issues two fully coalesced 128-bit loads per thread.
+//
+// The reduction exploits the Pasta moduli: m = 1 (mod 2^32) so the Montgomery quotient
+// digit is simply -t0, limb 0 of m is 1, limbs 4..6 are 0 and limb 7 is 2^30, so each reduction row costs three
+// real multiply-adds plus a shift.
+//
+// Replaces (on device) pasta_curves `Fp`/`Fq` as used by halo2_proofs under taiga_halo2/src/proof.rs:33-40.
+#pragma once
+#include <cstdint>
+
+#ifdef __CUDACC__
+#define TB_HD __host__ __device__ __forceinline__
+#else
+#define TB_HD inline
+#endif
+
+namespace tb {
+
+struct FpParams {  // Pallas base field = Vesta scalar field = circuit field
+  static TB_HD constexpr uint32_t m(int i) {
+    return i == 0 ? 0x00000001u : i == 1 ? 0x992d30edu : i == 2 ? 0x094cf91bu : i == 3 ? 0x224698fcu : i == 7 ? 0x40000000u : 0u;
+  }
+  // R mod p, R^2 mod p
+  static TB_HD constexpr uint32_t r(int i) {
+    return i == 0 ? 0xfffffffdu : i == 1 ? 0x34786d38u : i == 2 ? 0xe41914adu : i == 3 ? 0x992c350bu : i == 7 ? 0x3fffffffu : 0xffffffffu;
+  }
+  static TB_HD constexpr uint32_t r2(int i) {
+    return i == 0 ? 0x0000000fu : i == 1 ? 0x8c78ecb3u : i == 2 ? 0x8b0de0e7u : i == 3 ? 0xd7d30dbdu : i == 4 ? 0xc3c95d18u : i == 5 ? 0x7797a99bu : i == 6 ? 0x7b9cb714u : 0x096d41afu;
+  }
+  static constexpr int id = 0;
+};
+struct FqParams {  // Vesta base field = Pallas scalar field
+  static TB_HD constexpr uint32_t m(int i) {
+    return i == 0 ? 0x00000001u : i == 1 ? 0x8c46eb21u : i == 2 ? 0x0994a8ddu : i == 3 ? 0x224698fcu : i == 7 ? 0x40000000u : 0u;
+  }
+  static TB_HD constexpr uint32_t r(int i) {
+    return i == 0 ? 0xfffffffdu : i == 1 ? 0x5b2b3e9cu : i == 2 ? 0xe3420567u : i == 3 ? 0x992c350bu : i == 7 ? 0x3fffffffu : 0xffffffffu;
+  }
+  static TB_HD constexpr uint32_t r2(int i) {
+    return i == 0 ? 0x0000000fu : i == 1 ? 0xfc9678ffu : i == 2 ? 0x891a16e3u : i == 3 ? 0x67bb433du : i == 4 ? 0x04ccf590u : i == 5 ? 0x7fae2310u : i == 6 ? 0x7ccfdaa9u : 0x096d41afu;
+  }
+  static constexpr int id = 1;
+};
+
+template <class P>
+struct alignas(16) Fe {
+  uint32_t l[8];
+
+  static TB_HD Fe zero() { Fe z;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z.l[i] = 0; return z; }
+  static TB_HD Fe one() { Fe o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.l[i] = P::r(i); return o; }
+  static TB_HD Fe r2() { Fe o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.l[i] = P::r2(i); return o; }
+  static TB_HD Fe raw_one() { Fe o = zero(); o.l[0] = 1; return o; }
+
+  TB_HD bool is_zero() const { uint32_t a = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a |= l[i]; return a == 0; }
+  TB_HD bool operator==(const Fe& o) const { uint32_t a = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a |= l[i] ^ o.l[i]; return a == 0; }
+  TB_HD bool operator!=(const Fe& o) const { return !(*this == o); }
+
+  // r = a - m if a >= m (a < 2m)
+  static TB_HD void cond_sub(uint32_t* a) {
+    uint32_t t[8]; uint64_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { uint64_t d = (uint64_t)a[i] - P::m(i) - br; t[i] = (uint32_t)d; br = (d >> 32) & 1; }
+    if (!br) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = t[i];
+    }
+  }
+  friend TB_HD Fe operator+(const Fe& a, const Fe& b) {
+    Fe r; uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c += (uint64_t)a.l[i] + b.l[i]; r.l[i] = (uint32_t)c; c >>= 32; }
+    cond_sub(r.l);  // a+b < 2m < 2^256: no carry out
+    return r;
+  }
+  friend TB_HD Fe operator-(const Fe& a, const Fe& b) {
+    Fe r; uint64_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { uint64_t d = (uint64_t)a.l[i] - b.l[i] - br; r.l[i] = (uint32_t)d; br = (d >> 32) & 1; }
+    uint32_t mask = (uint32_t)0 - (uint32_t)br; uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c += (uint64_t)r.l[i] + (P::m(i) & mask); r.l[i] = (uint32_t)c; c >>= 32; }
+    return r;
+  }
+  TB_HD Fe neg() const { return zero() - *this; }
+  TB_HD Fe dbl() const { return *this + *this; }
+
+  // Montgomery product a*b*R^-1 mod m (CIOS, 32-bit limbs, Pasta-specific reduction row)
+  friend TB_HD Fe operator*(const Fe& a, const Fe& b) {
+    uint32_t t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = 0;
+    uint32_t t8 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint64_t c = 0;
+      const uint32_t bi = b.l[i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c += (uint64_t)a.l[j] * bi + t[j]; t[j] = (uint32_t)c; c >>= 32; }
+      c += t8; t8 = (uint32_t)c; uint32_t t9 = (uint32_t)(c >> 32);
+      // reduction row: q = -t0 (since -m^-1 = -1 mod 2^32); t = (t + q*m) >> 32
+      const uint32_t q = 0u - t[0];
+      c = (t[0] != 0) ? 1 : 0;  // (t0 + q*1) >> 32
+      c += (uint64_t)q * P::m(1) + t[1]; t[0] = (uint32_t)c; c >>= 32;
+      c += (uint64_t)q * P::m(2) + t[2]; t[1] = (uint32_t)c; c >>= 32;
+      c += (uint64_t)q * P::m(3) + t[3]; t[2] = (uint32_t)c; c >>= 32;
+      c += t[4]; t[3] = (uint32_t)c; c >>= 32;
+      c += t[5]; t[4] = (uint32_t)c; c >>= 32;
+      c += t[6]; t[5] = (uint32_t)c; c >>= 32;
+      c += ((uint64_t)q << 30) + t[7]; t[6] = (uint32_t)c; c >>= 32;  // q * 2^30 at limb 7
+      c += t8; t[7] = (uint32_t)c; t8 = t9 + (uint32_t)(c >> 32);
+    }
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = t[i];
+    cond_sub(r.l);  // result < 2m, t8 == 0
+    return r;
+  }
+  TB_HD Fe sqr() const { return (*this) * (*this); }
+
+  TB_HD Fe to_mont() const { return (*this) * r2(); }        // canonical -> Montgomery
+  TB_HD Fe from_mont() const { return (*this) * raw_one(); }  // Montgomery -> canonical
+
+  static TB_HD Fe from_u32(uint32_t v) { Fe a = zero(); a.l[0] = v; return a.to_mont(); }
+
+  // exponent as 8 LE 32-bit limbs
+  TB_HD Fe pow(const uint32_t* e, int nlimbs) const {
+    Fe acc = one();
+    for (int i = nlimbs - 1; i >= 0; --i)
+      for (int b = 31; b >= 0; --b) { acc = acc.sqr(); if ((e[i] >> b) & 1) acc = acc * (*this); }
+    return acc;
+  }
+  TB_HD Fe pow_u64(uint64_t e) const { uint32_t w[2] = {(uint32_t)e, (uint32_t)(e >> 32)}; return pow(w, 2); }
+  // Fermat inversion, 0 -> 0
+  TB_HD Fe inv() const {
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = P::m(i);
+    e[0] -= 2;  // m(0) == 1 -> borrow
+    e[0] = 0xffffffffu; e[1] = P::m(1) - 1;
+    return pow(e, 8);
+  }
+  // canonical-integer comparison of two canonical (non-Montgomery) values
+  static TB_HD int cmp_raw(const Fe& a, const Fe& b) {
+    for (int i = 7; i >= 0; --i) { if (a.l[i] < b.l[i]) return -1; if (a.l[i] > b.l[i]) return 1; }
+    return 0;
+  }
+};
+
+typedef Fe<FpParams> Fp;
+typedef Fe<FqParams> Fq;
+
+}  // namespace tb
