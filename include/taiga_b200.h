@@ -1,0 +1,78 @@
+/* taiga_b200.h - C ABI of libtaiga_b200.so, the B200-native (sm_100a) prover hot path for anoma/taiga.
+ *
+ * The reference has NO FFI on this path: the seam is the Rust call
+ *     taiga_halo2/src/proof.rs:25-42   Proof::create(pk, params, circuit, instance, rng) -> Result<Proof, plonk::Error>
+ * which forwards to halo2_proofs::plonk::create_proof (un-vendored git dependency, taiga_halo2/Cargo.toml:14-15).
+ * This header is what a Rust shim (cc + bindgen) binds in place of that body.
+ *
+ * Conventions
+ *   - field element: 32 bytes, little-endian canonical integer < modulus (what `to_repr()` returns in Rust).
+ *   - point: 64 bytes affine x||y (each a field element of the curve's base field); identity = 64 zero bytes
+ *     (the coordinates `vesta::Affine` holds, taiga_halo2/src/proof.rs:26).
+ *   - field ids : TB_FP = circuit field (pallas::Base = vesta::Scalar), TB_FQ = vesta::Base.
+ *   - curve ids : TB_VESTA = commitment curve of Taiga's proofs (base Fq, scalars Fp), TB_PALLAS (base Fp, scalars Fq).
+ *   - every call returns tb_status (0 = OK); nothing throws or panics across the ABI; the message for the last
+ *     failure on a context is available from tb_last_error().  A tb_ctx is bound to one GPU and one host thread.
+ *   - there is no CPU fallback: every entry point fails with TB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef TAIGA_B200_H
+#define TAIGA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int tb_status;
+enum { TB_OK = 0, TB_ERR_INVALID = 1, TB_ERR_CUDA = 2, TB_ERR_CONSTRAINT = 3, TB_ERR_INTERNAL = 4 };
+enum { TB_FP = 0, TB_FQ = 1 };
+enum { TB_VESTA = 0, TB_PALLAS = 1 };
+
+typedef struct tb_ctx tb_ctx;
+typedef struct tb_srs tb_srs;
+
+/* ---- context (owns a CUDA stream, twiddle tables, stream-ordered scratch memory) */
+tb_status tb_ctx_create(int device, tb_ctx** out);
+void tb_ctx_destroy(tb_ctx* ctx);
+const char* tb_last_error(const tb_ctx* ctx);
+const char* tb_version(void);
+tb_status tb_ctx_sync(tb_ctx* ctx);
+uint64_t tb_ctx_stream(const tb_ctx* ctx);        /* cudaStream_t, for event timing by the caller */
+uint64_t tb_ctx_launch_count(const tb_ctx* ctx);  /* kernels launched through this context so far */
+
+/* ---- primitives over HOST buffers (copies in and out inside the call).
+ * tb_ntt   replaces halo2_proofs arithmetic::best_fft / EvaluationDomain::{lagrange_to_coeff, coeff_to_lagrange}
+ *          (EXT; reached from taiga_halo2/src/proof.rs:33-40).  inverse != 0 also scales by 1/n.
+ *          coset: 0 = plain; 1 = halo2 zeta-coset (input coefficient i pre-scaled by ZETA^(i mod 3) for the forward
+ *          transform, output coefficient i post-scaled by ZETA^-(i mod 3) for the inverse one).
+ * tb_msm   replaces halo2_proofs arithmetic::best_multiexp (EXT).  `batch` scalar vectors share one base vector.
+ *          window_bits = 0 selects the default window. */
+tb_status tb_ntt(tb_ctx* ctx, int field, uint32_t logn, int inverse, int coset, uint32_t batch, const uint8_t* in, uint8_t* out);
+tb_status tb_msm(tb_ctx* ctx, int curve, size_t n, uint32_t batch, const uint8_t* scalars, const uint8_t* points,
+                 uint32_t window_bits, uint8_t* out_points);
+
+/* ---- the same primitives over DEVICE memory owned by the caller (e.g. torch tensors).  Device field elements
+ * are 32-byte Montgomery residues (R = 2^256); convert with tb_dev_{to,from}_mont.  Work is enqueued on the
+ * context's stream; call tb_ctx_sync (or wait on the stream) before reading results. */
+tb_status tb_dev_to_mont(tb_ctx* ctx, int field, void* d_elems, size_t n);
+tb_status tb_dev_from_mont(tb_ctx* ctx, int field, void* d_elems, size_t n);
+tb_status tb_dev_ntt(tb_ctx* ctx, int field, uint32_t logn, int inverse, int coset, uint32_t batch, const void* d_in, void* d_out,
+                     void* d_scratch /* batch << logn elements; may alias d_in if the input may be destroyed */);
+tb_status tb_dev_msm(tb_ctx* ctx, int curve, size_t n, uint32_t batch, const void* d_scalars, const void* d_points,
+                     uint32_t window_bits, void* d_out_points /* batch affine points, Montgomery */);
+
+/* ---- structured reference string.  Replaces halo2_proofs poly::commitment::Params<vesta::Affine> as held in
+ * SETUP_PARAMS_MAP (taiga_halo2/src/constant.rs:128-139).  g / g_lagrange: 2^k affine points each; w, u: one point.
+ * The call copies everything to the device and precomputes the fixed-base window tables. */
+tb_status tb_srs_load(tb_ctx* ctx, uint32_t k, const uint8_t* g, const uint8_t* g_lagrange, const uint8_t* w, const uint8_t* u,
+                      tb_srs** out);
+void tb_srs_free(tb_srs* srs);
+/* Params::commit (lagrange = 0) / Params::commit_lagrange (lagrange = 1):  out[b] = MSM(scalars[b], basis) + blinds[b] * w.
+ * blinds may be NULL (no blinding term). */
+tb_status tb_srs_commit(tb_ctx* ctx, const tb_srs* srs, int lagrange, uint32_t batch, const uint8_t* scalars, const uint8_t* blinds,
+                        uint8_t* out_points);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAIGA_B200_H */

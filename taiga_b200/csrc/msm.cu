@@ -1,0 +1,295 @@
+// Pippenger multi-scalar multiplication over the Pasta curves for sm_100a.
+//
+// Replaces halo2_proofs `arithmetic::best_multiexp` and `Params::{commit, commit_lagrange}` (EXT, called under
+// taiga_halo2/src/proof.rs:33-40).  Two modes share one pipeline:
+//   * variable-base (standalone sweep, IPA rounds): W = ceil(256/c) windows, one bucket set per window;
+//   * fixed-base (every commitment of the prover: bases are the SRS `g` / `g_lagrange`): the bases were premultiplied
+//     by 2^(c*w) at SRS load, so all windows share ONE bucket set and the final Horner over windows disappears.
+// Pipeline: signed-digit extraction + bucket histogram -> exclusive scan -> scatter of (point index, sign) into
+// bucket-sorted order -> bucket accumulation (one thread per <=64-entry unit, XYZZ mixed adds; oversized buckets are
+// split into units and combined by a CTA with warp-shuffle reduction) -> per-window running-sum reduction (segments,
+// warp-shuffle tree) -> Horner over windows.
+//
+// Algorithmic bytes: 96*N per MSM (64 B affine base + 32 B scalar); fixed-base batched: 64*N*W (tables) + 32*N*K.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace tb {
+
+constexpr int MSM_CHUNK = 64;   // max entries accumulated by one thread
+constexpr int MSM_SEG = 32;     // buckets per thread in the running-sum reduction
+
+int msm_default_window(int n, bool fixed_tables) {
+  if (fixed_tables) return 16;
+  int lg = 0; while ((1 << (lg + 1)) <= n) ++lg;
+  int c = lg - 4;
+  if (c < 4) c = 4;
+  if (c > 16) c = 16;
+  return c;
+}
+
+__device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int bit, int c) {
+  int limb = bit >> 5, off = bit & 31;
+  uint64_t v = s[limb];
+  if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
+  return (uint32_t)(v >> off) & ((1u << c) - 1);
+}
+
+// MODE 0: histogram, MODE 1: scatter
+template <class S, int MODE>
+__global__ void msm_digits_kernel(const S* __restrict__ scalars, long long sstride, int N, int c, int W, int NB, int wsep,
+                                  int table_mode, uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int k = blockIdx.y;
+  if (i >= N) return;
+  S s = ldg_fe(scalars + (long long)k * sstride + i).from_mont();
+  if (s.is_zero()) return;
+  const uint32_t half = 1u << (c - 1);
+  uint32_t carry = 0;
+  for (int w = 0; w < W; ++w) {
+    uint32_t v = window_bits(s.l, w * c, c) + carry;
+    uint32_t neg = 0;
+    if (v > half) { v = (1u << c) - v; neg = 1; carry = 1; } else carry = 0;
+    if (v) {
+      uint32_t b = ((uint32_t)k * wsep + (wsep > 1 ? w : 0)) * NB + (v - 1);
+      if (MODE == 0) atomicAdd(&counts_or_cursor[b], 1u);
+      else {
+        uint32_t pos = atomicAdd(&counts_or_cursor[b], 1u);
+        entries[pos] = (table_mode ? (uint32_t)(w * N + i) : (uint32_t)i) | (neg << 31);
+      }
+    }
+  }
+}
+
+// units per bucket; buckets with more than one unit are appended to the heavy list
+__global__ void msm_units_kernel(const uint32_t* __restrict__ offs, uint32_t nb_total, uint32_t* __restrict__ unit_count,
+                                 uint32_t* __restrict__ heavy, uint32_t* __restrict__ n_heavy) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb_total) return;
+  uint32_t cnt = offs[b + 1] - offs[b];
+  uint32_t uc = (cnt + MSM_CHUNK - 1) / MSM_CHUNK;
+  unit_count[b] = uc;
+  if (uc > 1) heavy[atomicAdd(n_heavy, 1u)] = b;
+}
+
+template <class B>
+__global__ void __launch_bounds__(128) msm_accum_kernel(const Aff<B>* __restrict__ bases, long long base_bstride, uint32_t buckets_per_item,
+                                 const uint32_t* __restrict__ offs, const uint32_t* __restrict__ unit_off, uint32_t nb_total,
+                                 const uint32_t* __restrict__ entries, Xyzz<B>* __restrict__ partial) {
+  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= unit_off[nb_total]) return;
+  // largest b with unit_off[b] <= u
+  uint32_t lo = 0, hi = nb_total;
+  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (unit_off[mid] <= u) lo = mid; else hi = mid; }
+  uint32_t b = lo, j = u - unit_off[b];
+  uint32_t beg = offs[b] + j * MSM_CHUNK, end = offs[b + 1];
+  if (end > beg + MSM_CHUNK) end = beg + MSM_CHUNK;
+  const Aff<B>* pts = bases + (long long)(b / buckets_per_item) * base_bstride;
+  Xyzz<B> acc = Xyzz<B>::inf();
+  for (uint32_t e = beg; e < end; ++e) {
+    uint32_t pl = __ldg(entries + e);
+    Aff<B> p = ldg_aff(pts + (pl & 0x7fffffffu));
+    if (pl >> 31) p.y = p.y.neg();
+    acc.add_affine(p);
+  }
+  partial[u] = acc;
+}
+
+template <class B> __device__ __forceinline__ Xyzz<B> shfl_down_pt(const Xyzz<B>& p, int delta) {
+  Xyzz<B> r;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&p);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) dst[i] = __shfl_down_sync(0xffffffffu, src[i], delta);
+  return r;
+}
+
+// sum over a 256-thread CTA; result valid in thread 0
+template <class B> __device__ Xyzz<B> block_reduce_pt(Xyzz<B> v, Xyzz<B>* sm /* 8 slots */) {
+  for (int d = 16; d >= 1; d >>= 1) { Xyzz<B> o = shfl_down_pt(v, d); v.add(o); }
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = (lane < (int)(blockDim.x >> 5)) ? sm[lane] : Xyzz<B>::inf();
+    for (int d = 4; d >= 1; d >>= 1) { Xyzz<B> o = shfl_down_pt(v, d); v.add(o); }
+  }
+  return v;
+}
+
+// one CTA per oversized bucket: fold its units' partial sums into the first unit's slot
+template <class B>
+__global__ void __launch_bounds__(256) msm_heavy_kernel(const uint32_t* __restrict__ heavy, const uint32_t* __restrict__ n_heavy,
+                                                         const uint32_t* __restrict__ unit_off, Xyzz<B>* __restrict__ partial) {
+  __shared__ Xyzz<B> sm[8];
+  uint32_t nh = *n_heavy;
+  for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+    uint32_t b = heavy[h], u0 = unit_off[b], u1 = unit_off[b + 1];
+    Xyzz<B> acc = Xyzz<B>::inf();
+    for (uint32_t u = u0 + threadIdx.x; u < u1; u += blockDim.x) acc.add(partial[u]);
+    acc = block_reduce_pt(acc, sm);
+    __syncthreads();
+    if (threadIdx.x == 0) partial[u0] = acc;
+    __syncthreads();
+  }
+}
+
+// running-sum reduction of one segment of MSM_SEG buckets: sum_b (b+1) * bucket_b restricted to the segment
+template <class B>
+__global__ void __launch_bounds__(128) msm_segsum_kernel(const uint32_t* __restrict__ unit_off, const Xyzz<B>* __restrict__ partial,
+                                                          int NB, int seg, int nt, uint32_t groups, Xyzz<B>* __restrict__ seg_out) {
+  uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= groups * (uint32_t)nt) return;
+  uint32_t g = id / nt, t = id % nt;
+  uint32_t b0 = g * NB + t * seg;
+  Xyzz<B> run = Xyzz<B>::inf(), acc = Xyzz<B>::inf();
+  for (int j = seg - 1; j >= 0; --j) {
+    uint32_t b = b0 + j;
+    uint32_t u0 = unit_off[b];
+    if (unit_off[b + 1] != u0) run.add(partial[u0]);
+    acc.add(run);
+  }
+  // + (t*seg) * run
+  uint32_t m = t * seg;
+  if (m && !run.is_inf()) {
+    Xyzz<B> r = Xyzz<B>::inf();
+    for (int bit = 31 - __clz(m); bit >= 0; --bit) { r = r.dbl(); if ((m >> bit) & 1) r.add(run); }
+    acc.add(r);
+  }
+  seg_out[id] = acc;
+}
+
+template <class B>
+__global__ void __launch_bounds__(256) msm_window_kernel(const Xyzz<B>* __restrict__ seg_out, int nt, Xyzz<B>* __restrict__ win_out) {
+  __shared__ Xyzz<B> sm[8];
+  uint32_t g = blockIdx.x;
+  Xyzz<B> acc = Xyzz<B>::inf();
+  for (int t = threadIdx.x; t < nt; t += blockDim.x) acc.add(seg_out[(size_t)g * nt + t]);
+  acc = block_reduce_pt(acc, sm);
+  if (threadIdx.x == 0) win_out[g] = acc;
+}
+
+template <class B>
+__global__ void msm_horner_kernel(const Xyzz<B>* __restrict__ win, int wsep, int c, int K, Xyzz<B>* __restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  Xyzz<B> acc = win[(size_t)k * wsep + wsep - 1];
+  for (int w = wsep - 2; w >= 0; --w) {
+    for (int i = 0; i < c; ++i) acc = acc.dbl();
+    acc.add(win[(size_t)k * wsep + w]);
+  }
+  out[k] = acc;
+}
+
+template <class B, class S>
+void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>* bases, long long base_bstride, int N, int K,
+             const MsmConfig& cfg_in, Xyzz<B>* out) {
+  TB_REQUIRE(N >= 1 && K >= 1 && K <= 65535, "MSM shape out of range");
+  const bool table_mode = cfg_in.table_windows > 0;
+  int c = cfg_in.c ? cfg_in.c : msm_default_window(N, table_mode);
+  TB_REQUIRE(c >= 2 && c <= 20, "MSM window out of range");
+  const int W = (256 + c - 1) / c;
+  if (table_mode) TB_REQUIRE(cfg_in.table_windows >= W, "fixed-base table has too few windows");
+  const int NB = 1 << (c - 1);
+  const int wsep = table_mode ? 1 : W;
+  const uint64_t nb_total64 = (uint64_t)K * wsep * NB;
+  const uint64_t max_entries = (uint64_t)K * N * W;
+  TB_REQUIRE(nb_total64 < (1ull << 31) && max_entries < (1ull << 32) && (uint64_t)N * (table_mode ? W : 1) < (1ull << 31), "MSM too large");
+  const uint32_t nb_total = (uint32_t)nb_total64;
+  cudaStream_t st = ctx->stream;
+
+  DevBuf<uint32_t> counts(ctx, nb_total), offs(ctx, nb_total + 1), cursor(ctx, nb_total), entries(ctx, max_entries);
+  counts.zero();
+  dim3 dg((N + 255) / 256, K);
+  msm_digits_kernel<S, 0><<<dg, 256, 0, st>>>(scalars, scalar_bstride, N, c, W, NB, wsep, table_mode, counts.get(), nullptr);
+  TB_LAUNCH_CHECK();
+  exclusive_scan_u32(ctx, counts.get(), offs.get(), nb_total);
+  TB_CUDA(cudaMemcpyAsync(cursor.get(), offs.get(), nb_total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  msm_digits_kernel<S, 1><<<dg, 256, 0, st>>>(scalars, scalar_bstride, N, c, W, NB, wsep, table_mode, cursor.get(), entries.get());
+  TB_LAUNCH_CHECK();
+
+  const uint64_t max_heavy = max_entries / MSM_CHUNK + 1;
+  const uint64_t max_units = nb_total64 + max_heavy;
+  DevBuf<uint32_t> unit_count(ctx, nb_total), unit_off(ctx, nb_total + 1), heavy(ctx, max_heavy), n_heavy(ctx, 1);
+  n_heavy.zero();
+  msm_units_kernel<<<(nb_total + 255) / 256, 256, 0, st>>>(offs.get(), nb_total, unit_count.get(), heavy.get(), n_heavy.get());
+  TB_LAUNCH_CHECK();
+  exclusive_scan_u32(ctx, unit_count.get(), unit_off.get(), nb_total);
+  DevBuf<Xyzz<B>> partial(ctx, max_units);
+  msm_accum_kernel<B><<<(unsigned)((max_units + 127) / 128), 128, 0, st>>>(bases, base_bstride, (uint32_t)wsep * NB, offs.get(), unit_off.get(),
+                                                                          nb_total, entries.get(), partial.get());
+  TB_LAUNCH_CHECK();
+  unsigned hgrid = (unsigned)(max_heavy < 1184 ? max_heavy : 1184);
+  msm_heavy_kernel<B><<<hgrid, 256, 0, st>>>(heavy.get(), n_heavy.get(), unit_off.get(), partial.get());
+  TB_LAUNCH_CHECK();
+
+  const int seg = NB < MSM_SEG ? NB : MSM_SEG;
+  const int nt = NB / seg;
+  const uint32_t groups = (uint32_t)K * wsep;
+  DevBuf<Xyzz<B>> seg_out(ctx, (size_t)groups * nt), win(ctx, groups);
+  msm_segsum_kernel<B><<<(groups * nt + 127) / 128, 128, 0, st>>>(unit_off.get(), partial.get(), NB, seg, nt, groups, seg_out.get());
+  TB_LAUNCH_CHECK();
+  if (wsep == 1) {
+    msm_window_kernel<B><<<groups, 256, 0, st>>>(seg_out.get(), nt, out);
+    TB_LAUNCH_CHECK();
+    ctx->launches += 7;
+  } else {
+    msm_window_kernel<B><<<groups, 256, 0, st>>>(seg_out.get(), nt, win.get());
+    TB_LAUNCH_CHECK();
+    msm_horner_kernel<B><<<(K + 31) / 32, 32, 0, st>>>(win.get(), wsep, c, K, out);
+    TB_LAUNCH_CHECK();
+    ctx->launches += 8;
+  }
+}
+
+template void msm_run<Fq, Fp>(Ctx*, const Fp*, long long, const Aff<Fq>*, long long, int, int, const MsmConfig&, Xyzz<Fq>*);
+template void msm_run<Fp, Fq>(Ctx*, const Fq*, long long, const Aff<Fp>*, long long, int, int, const MsmConfig&, Xyzz<Fp>*);
+
+// ---------------------------------------------------------------- fixed-base tables
+template <class B>
+__global__ void msm_table_step_kernel(const Aff<B>* __restrict__ prev, Aff<B>* __restrict__ next, int N, int c) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  Xyzz<B> p = Xyzz<B>::from_affine(prev[i]);
+  for (int j = 0; j < c; ++j) p = p.dbl();
+  next[i] = p.to_affine();
+}
+
+template <class B>
+void msm_build_tables(Ctx* ctx, const Aff<B>* bases, int N, int c, int windows, Aff<B>* table) {
+  TB_CUDA(cudaMemcpyAsync(table, bases, (size_t)N * sizeof(Aff<B>), cudaMemcpyDeviceToDevice, ctx->stream));
+  for (int w = 1; w < windows; ++w) {
+    msm_table_step_kernel<B><<<(N + 127) / 128, 128, 0, ctx->stream>>>(table + (size_t)(w - 1) * N, table + (size_t)w * N, N, c);
+    TB_LAUNCH_CHECK();
+  }
+}
+template void msm_build_tables<Fq>(Ctx*, const Aff<Fq>*, int, int, int, Aff<Fq>*);
+template void msm_build_tables<Fp>(Ctx*, const Aff<Fp>*, int, int, int, Aff<Fp>*);
+
+// ---------------------------------------------------------------- finalisation: + sum extra_scalar * extra_base, to affine
+template <class B, class S>
+__global__ void points_finalize_kernel(const Xyzz<B>* __restrict__ acc, int K, const S* __restrict__ extra_scalars,
+                                       const Aff<B>* __restrict__ extra_bases, int n_extra, Aff<B>* __restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  Xyzz<B> p = acc[k];
+  for (int j = 0; j < n_extra; ++j) {
+    S s = extra_scalars[(size_t)k * n_extra + j].from_mont();
+    if (s.is_zero()) continue;
+    Xyzz<B> t = scalar_mul(extra_bases[j], s.l);
+    p.add(t);
+  }
+  out[k] = p.to_affine();
+}
+
+template <class B, class S>
+void points_finalize(Ctx* ctx, const Xyzz<B>* acc, int K, const S* extra_scalars, const Aff<B>* extra_bases, int n_extra, Aff<B>* out) {
+  points_finalize_kernel<B, S><<<(K + 31) / 32, 32, 0, ctx->stream>>>(acc, K, extra_scalars, extra_bases, n_extra, out);
+  TB_LAUNCH_CHECK();
+  ctx->launches++;
+}
+template void points_finalize<Fq, Fp>(Ctx*, const Xyzz<Fq>*, int, const Fp*, const Aff<Fq>*, int, Aff<Fq>*);
+template void points_finalize<Fp, Fq>(Ctx*, const Xyzz<Fp>*, int, const Fq*, const Aff<Fp>*, int, Aff<Fp>*);
+
+}  // namespace tb

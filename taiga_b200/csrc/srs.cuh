@@ -1,0 +1,64 @@
+// Device-resident structured reference string with fixed-base window tables.
+// Replaces halo2_proofs `poly::commitment::Params<vesta::Affine>` (EXT) as loaded by SETUP_PARAMS_MAP
+// (taiga_halo2/src/constant.rs:128-139) and its `commit` / `commit_lagrange` methods.
+#pragma once
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace tb {
+
+struct Srs {
+  Ctx* ctx = nullptr;
+  uint32_t k = 0; size_t n = 0;
+  int c = 16, W = 16;                       // fixed-base window bits / number of table windows
+  Aff<Fq>* g = nullptr;                      // [n]   (device, Montgomery)
+  Aff<Fq>* g_lagrange = nullptr;             // [n]
+  Aff<Fq>* tab_g = nullptr;                  // [W][n]  2^(c*w) * g[i]
+  Aff<Fq>* tab_gl = nullptr;                 // [W][n]
+  Aff<Fq>* wu = nullptr;                     // [2] = {w, u}
+  Aff<Fq> w_host, u_host;                    // Montgomery
+
+  static Srs* load(Ctx* ctx, uint32_t k, const uint8_t* g, const uint8_t* gl, const uint8_t* w, const uint8_t* u) {
+    Srs* s = new Srs();
+    s->ctx = ctx; s->k = k; s->n = size_t(1) << k;
+    int c = (int)k + 1; if (c < 4) c = 4; if (c > 16) c = 16;
+    s->c = c; s->W = (256 + c - 1) / c;
+    size_t n = s->n;
+    try {
+      TB_CUDA(cudaMalloc(&s->g, n * sizeof(Aff<Fq>)));
+      TB_CUDA(cudaMalloc(&s->g_lagrange, n * sizeof(Aff<Fq>)));
+      TB_CUDA(cudaMalloc(&s->tab_g, (size_t)s->W * n * sizeof(Aff<Fq>)));
+      TB_CUDA(cudaMalloc(&s->tab_gl, (size_t)s->W * n * sizeof(Aff<Fq>)));
+      TB_CUDA(cudaMalloc(&s->wu, 2 * sizeof(Aff<Fq>)));
+      TB_CUDA(cudaMemcpyAsync(s->g, g, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+      TB_CUDA(cudaMemcpyAsync(s->g_lagrange, gl, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+      TB_CUDA(cudaMemcpyAsync(s->wu, w, 64, cudaMemcpyHostToDevice, ctx->stream));
+      TB_CUDA(cudaMemcpyAsync(s->wu + 1, u, 64, cudaMemcpyHostToDevice, ctx->stream));
+      fe_to_mont<Fq>(ctx, reinterpret_cast<Fq*>(s->g), 2 * n);
+      fe_to_mont<Fq>(ctx, reinterpret_cast<Fq*>(s->g_lagrange), 2 * n);
+      fe_to_mont<Fq>(ctx, reinterpret_cast<Fq*>(s->wu), 4);
+      msm_build_tables<Fq>(ctx, s->g, (int)n, c, s->W, s->tab_g);
+      msm_build_tables<Fq>(ctx, s->g_lagrange, (int)n, c, s->W, s->tab_gl);
+      Aff<Fq> h[2];
+      TB_CUDA(cudaMemcpyAsync(h, s->wu, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->sync();
+      s->w_host = h[0]; s->u_host = h[1];
+    } catch (...) { delete s; throw; }
+    return s;
+  }
+  ~Srs() { cudaFree(g); cudaFree(g_lagrange); cudaFree(tab_g); cudaFree(tab_gl); cudaFree(wu); }
+
+  // acc[k] = MSM(scalars_k, basis) via the fixed-base tables (no blinding term, no normalisation)
+  void commit_xyzz(Ctx* c_, bool lagrange, const Fp* scalars, long long stride, int K, Xyzz<Fq>* acc) const {
+    MsmConfig cfg; cfg.c = c; cfg.table_windows = W;
+    msm_run<Fq, Fp>(c_, scalars, stride, lagrange ? tab_gl : tab_g, 0, (int)n, K, cfg, acc);
+  }
+  // out[k] = affine(MSM(scalars_k, basis) + blinds[k] * w)
+  void commit(Ctx* c_, bool lagrange, const Fp* scalars, long long stride, int K, const Fp* blinds, Aff<Fq>* out) const {
+    DevBuf<Xyzz<Fq>> acc(c_, K);
+    commit_xyzz(c_, lagrange, scalars, stride, K, acc.get());
+    points_finalize<Fq, Fp>(c_, acc.get(), K, blinds, wu, blinds ? 1 : 0, out);
+  }
+};
+
+}  // namespace tb

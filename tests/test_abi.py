@@ -1,0 +1,34 @@
+"""CPU: the C-ABI shared library loads here (no GPU) and exports every symbol include/taiga_b200.h declares;
+without a device every entry point fails loudly instead of falling back to the CPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from taiga_b200 import lib
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "taiga_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(tb_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported():
+    assert os.path.exists(lib.LIB_PATH), "libtaiga_b200.so must be built in-tree (see __graft_entry__.build)"
+    so = ctypes.CDLL(lib.LIB_PATH)
+    declared = _declared()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(so, name), name
+    assert declared == lib.exported_symbols()
+
+
+def test_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(lib.TaigaB200Error):
+        lib.Context(0)

@@ -1,0 +1,123 @@
+"""CPU: pins the oracle (oracle/pasta.py big-int model and oracle/liboracle.so threaded C++ restatement) against
+each other and against the reference's fixture params_15."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+
+from conftest import GOLDEN
+from oracle import pasta as o
+
+
+def test_field_constants(oracle_cpu):
+    c = oracle_cpu
+    for f, m, root, z, d in [(c.FP, o.P, o.ROOT_P, o.ZETA_P, o.DELTA_P), (c.FQ, o.Q, o.ROOT_Q, o.ZETA_Q, o.DELTA_Q)]:
+        k = c.field_consts(f, 15)
+        assert k["omega"] == pow(root, 1 << 17, m) and k["delta"] == d and k["zeta"] == z
+        assert k["R"] == (1 << 256) % m and k["R2"] == (1 << 512) % m and (k["inv64"] * m) % (1 << 64) == (1 << 64) - 1
+    # omega_15 of Fp
+    assert o.omega(15) == 0x2FD0767705FA5B03402039FC9E89AD1DE3C85D25401FD8DD898DCE603D1C0F3E
+    assert pow(o.omega(15), 1 << 15, o.P) == 1 and pow(o.omega(15), 1 << 14, o.P) != 1
+
+
+def test_field_ops_match_python(oracle_cpu):
+    c = oracle_cpu
+    rnd = random.Random(1)
+    for f, m in [(c.FP, o.P), (c.FQ, o.Q)]:
+        vals = [0, 1, m - 1, (1 << 256) % m, (1 << 255) % m, 2 ** 64 - 1] + [rnd.randrange(m) for _ in range(100)]
+        for a in vals:
+            b = rnd.choice(vals)
+            A, B = c.ints_to_bytes([a])[0], c.ints_to_bytes([b])[0]
+            assert c.bytes_to_ints(c.field_op(f, 0, A, B)[1])[0] == (a + b) % m
+            assert c.bytes_to_ints(c.field_op(f, 1, A, B)[1])[0] == (a - b) % m
+            assert c.bytes_to_ints(c.field_op(f, 2, A, B)[1])[0] == a * b % m
+        a = rnd.randrange(1, m)
+        assert c.bytes_to_ints(c.field_op(f, 3, c.ints_to_bytes([a])[0])[1])[0] == pow(a, m - 2, m)
+        rc, s = c.field_op(f, 4, c.ints_to_bytes([a * a % m])[0])
+        assert rc == 0 and c.bytes_to_ints(s)[0] in (a, m - a)
+        rc, _ = c.field_op(f, 4, c.ints_to_bytes([5])[0])  # 5 generates the multiplicative group: a non-residue
+        assert rc == 1
+        u = bytes(rnd.randrange(256) for _ in range(64))
+        assert c.bytes_to_ints(c.from_uniform(f, u))[0] == int.from_bytes(u, "little") % m
+
+
+def test_ntt_and_domain_match_python(oracle_cpu):
+    c = oracle_cpu
+    rnd = random.Random(2)
+    a = [rnd.randrange(o.P) for _ in range(256)]
+    A = c.ints_to_bytes(a)
+    assert c.bytes_to_ints(c.ntt(c.FP, A)) == o.ntt(a, o.omega(8)) == o.ntt_naive(a[:256], o.omega(8))
+    assert c.bytes_to_ints(c.ntt(c.FP, c.ntt(c.FP, A), inverse=True)) == a
+    ext = c.coeff_to_extended(8, 5, A)
+    assert c.bytes_to_ints(ext) == o.coeff_to_extended(a, 8, 10)
+    we = o.omega(10)
+    for j in (0, 1, 7, 1023):  # extended evaluations are evaluations on the zeta-coset
+        assert c.bytes_to_ints(ext[j])[0] == o.eval_poly(a, o.ZETA_P * pow(we, j, o.P) % o.P)
+    assert c.bytes_to_ints(c.extended_to_coeff(8, 5, ext))[:256] == a
+    b = [rnd.randrange(o.Q) for _ in range(64)]
+    assert c.bytes_to_ints(c.ntt(c.FQ, c.ints_to_bytes(b))) == o.ntt(b, o.omega(6, o.Q), o.Q)
+
+
+def test_curve_ops_match_python(oracle_cpu):
+    c = oracle_cpu
+    rnd = random.Random(3)
+    for cid, cv, G in [(c.VESTA, o.VESTA, o.VESTA_GEN), (c.PALLAS, o.PALLAS, o.PALLAS_GEN)]:
+        assert cv.is_on_curve(G)
+        pts = [cv.mul(rnd.randrange(cv.fs), G) for _ in range(12)]
+        sc = [rnd.randrange(cv.fs) for _ in range(12)]
+        sc[0], sc[1], sc[2] = 0, 1, cv.fs - 1
+        P_bytes = np.concatenate([c.ints_to_bytes(list(p)) for p in pts])
+        got = c.msm(cid, c.ints_to_bytes(sc), P_bytes)
+        assert c.bytes_to_ints(got.reshape(2, 32)) == list(cv.msm(sc, pts))
+        enc = c.compress(cid, P_bytes)
+        for e, p in zip(enc, pts):
+            assert e.tobytes() == cv.compress(p) and cv.decompress(e.tobytes()) == p
+        assert c.decompress(cid, enc).tobytes() == P_bytes.tobytes()
+        # group order annihilates
+        assert cv.mul(cv.fs, G) is None if False else cv.add(cv.mul(cv.fs - 1, G), G) is None
+
+
+def test_srs_fixture_matches_reference_digest(srs_fixture):
+    kat = json.load(open(os.path.join(GOLDEN, "srs_k15_kat.json")))
+    raw = np.fromfile(os.path.join(GOLDEN, "srs_k15_affine.bin"), dtype=np.uint8)
+    assert hashlib.sha256(raw.tobytes()).hexdigest() == kat["sha256_srs_k15_affine"]
+    assert kat["sum_g_lagrange_equals_g0"] and kat["ninv_sum_g_equals_g_lagrange0"] and kat["sum_omega_i_g_lagrange_i_equals_g1"]
+    g0 = srs_fixture["g"][0]
+    assert hex(int.from_bytes(g0[:32].tobytes(), "little")) == kat["g0_x"]
+    # g[0].x
+    assert kat["g0_x"] == "0x3decc7d8be779b2b8505a808c7e8109341ef95101391f5589738bf79d05e0645"
+    # compressed re-encoding reproduces the reference file byte for byte (checked through its sha256)
+    from oracle import cpu as c
+    enc = c.compress(c.VESTA, raw)
+    assert hashlib.sha256((15).to_bytes(4, "little") + enc.tobytes()).hexdigest() == kat["sha256_params_15"]
+
+
+def test_srs_identities_cpu_oracle(oracle_cpu, srs_fixture):
+    """The three identities of SURVEY B.2 + MSM(v, g_lagrange) == MSM(iNTT(v), g) for random v: ties point decoding,
+    Vesta arithmetic, the Lagrange-basis convention and the NTT direction / 1/n scaling to the reference's fixture."""
+    c, s = oracle_cpu, srs_fixture
+    n = s["n"]
+    for p in (s["g"][0], s["g"][n - 1], s["g_lagrange"][5], s["w"], s["u"]):
+        x, y = c.bytes_to_ints(p.reshape(2, 32))
+        assert o.VESTA.is_on_curve((x, y))
+    assert c.msm(c.VESTA, c.ints_to_bytes([1] * n), s["g_lagrange"]).tobytes() == s["g"][0].tobytes()
+    rnd = random.Random(4)
+    v = c.ints_to_bytes([rnd.randrange(o.P) for _ in range(n)])
+    assert c.msm(c.VESTA, v, s["g_lagrange"]).tobytes() == c.msm(c.VESTA, c.ntt(c.FP, v, inverse=True), s["g"]).tobytes()
+
+
+def test_transcript_model():
+    """halo2 Blake2b transcript conventions: prefix bytes and 64-byte squeeze reduced mod p."""
+    import hashlib as h
+    t = o.Transcript()
+    t.common_scalar(5)
+    t.write_point(o.VESTA_GEN)
+    ch = t.squeeze()
+    ref = h.blake2b(digest_size=64, person=b"Halo2-Transcript")
+    ref.update(b"\x02" + (5).to_bytes(32, "little"))
+    ref.update(b"\x01" + o.VESTA_GEN[0].to_bytes(32, "little") + o.VESTA_GEN[1].to_bytes(32, "little"))
+    ref.update(b"\x00")
+    assert ch == int.from_bytes(ref.digest(), "little") % o.P
+    assert bytes(t.proof) == o.VESTA.compress(o.VESTA_GEN)
