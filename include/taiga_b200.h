@@ -61,6 +61,35 @@ tb_status tb_dev_ntt(tb_ctx* ctx, int field, uint32_t logn, int inverse, int cos
 tb_status tb_dev_msm(tb_ctx* ctx, int curve, size_t n, uint32_t batch, const void* d_scalars, const void* d_points,
                      uint32_t window_bits, void* d_out_points /* batch affine points, Montgomery */);
 
+/* ---- circuit description.  Replaces what halo2_proofs keeps inside ProvingKey<vesta::Affine> / VerifyingKey.cs
+ * (COMPLIANCE_PROVING_KEY, taiga_halo2/src/constant.rs:145-152; TRIVIAL_RESOURCE_LOGIC_PK,
+ * taiga_halo2/src/circuit/resource_logic_examples.rs:50-61).  The Rust shim walks `pk.get_vk().cs()` once per circuit
+ * and fills this flat, pointer-based description; nothing here is Taiga specific. */
+typedef struct { uint32_t column; int32_t rotation; } tb_query;             /* (column index within its kind, Rotation) */
+enum { TB_COL_ADVICE = 0, TB_COL_FIXED = 1, TB_COL_INSTANCE = 2 };
+typedef struct { uint32_t kind; uint32_t index; } tb_column;                /* halo2 Column<Any> */
+/* halo2 `Expression<F>` flattened to a DAG in topological order (operands refer to earlier nodes):
+ *   CONST a=constant index | ADVICE/FIXED/INSTANCE a=index into the matching *_queries array | NEG a=node
+ *   ADD/MUL a,b=nodes | SCALE a=node, b=constant index.  (Selectors are already fixed columns after keygen.) */
+enum { TB_EX_CONST = 0, TB_EX_ADVICE = 1, TB_EX_FIXED = 2, TB_EX_INSTANCE = 3, TB_EX_NEG = 4, TB_EX_ADD = 5, TB_EX_MUL = 6, TB_EX_SCALE = 7 };
+typedef struct { uint32_t op, a, b; } tb_expr_node;
+typedef struct { uint32_t num_exprs; const uint32_t* input_roots; const uint32_t* table_roots; } tb_lookup;  /* lookup::Argument */
+typedef struct {
+  uint32_t k;                       /* rows = 2^k (PARAMS_SIZE = 15 for Taiga, constant.rs:123-125) */
+  uint32_t num_advice, num_fixed, num_instance;
+  uint32_t cs_degree;               /* cs.degree() */
+  uint32_t blinding_factors;        /* cs.blinding_factors() */
+  uint32_t num_advice_queries;   const tb_query* advice_queries;    /* cs.advice_queries, in order */
+  uint32_t num_fixed_queries;    const tb_query* fixed_queries;
+  uint32_t num_instance_queries; const tb_query* instance_queries;
+  uint32_t num_perm_columns;     const tb_column* perm_columns;     /* cs.permutation.columns, in order */
+  uint32_t num_constants;        const uint8_t* constants;          /* 32-byte field elements */
+  uint32_t num_nodes;            const tb_expr_node* nodes;
+  uint32_t num_constraints;      const uint32_t* constraint_roots;  /* every gate's polynomials, gate-major (halo2 order) */
+  uint32_t num_lookups;          const tb_lookup* lookups;
+  uint8_t vk_transcript_repr[32];  /* vk.transcript_repr (hash of the pinned vk; owned by the Rust side) */
+} tb_cs_desc;
+
 /* ---- structured reference string.  Replaces halo2_proofs poly::commitment::Params<vesta::Affine> as held in
  * SETUP_PARAMS_MAP (taiga_halo2/src/constant.rs:128-139).  g / g_lagrange: 2^k affine points each; w, u: one point.
  * The call copies everything to the device and precomputes the fixed-base window tables. */

@@ -137,3 +137,79 @@ def point_mul(curve, a, k_bytes):
     out = np.zeros(64, np.uint8)
     lib().orc_point_op(curve, 1, _p(_u8(a)), _p(_u8(k_bytes)), _p(out))
     return out
+
+
+# ---------------------------------------------------------------- halo2 prover / verifier restatement (oracle/plonk.cpp)
+class OracleKey:
+    """keygen result for one circuit (CircuitKeyData from taiga_b200.circuit) over an SRS dict of affine byte arrays."""
+
+    def __init__(self, keydata, srs):
+        L = lib()
+        L.orc_keygen.restype = ctypes.c_void_p
+        n = keydata.n
+        g, gl = _u8(srs["g"]), _u8(srs["g_lagrange"])
+        assert g.size == 64 * n and gl.size == 64 * n, "SRS size must match the circuit's k"
+        self.keydata, self.srs = keydata, srs
+        self._fixed, self._sigma = _u8(keydata.fixed), _u8(keydata.sigma)
+        self._h = ctypes.c_void_p(L.orc_keygen(ctypes.byref(keydata.desc), _p(g), _p(gl), _p(_u8(srs["w"])), _p(_u8(srs["u"])),
+                                               _p(self._fixed), _p(self._sigma)))
+
+    def prove(self, advice, instance, instance_len, seed, proof_index=0):
+        L = lib()
+        buf = np.zeros(1 << 16, np.uint8)
+        ln = ctypes.c_size_t(buf.size)
+        seed = _u8(np.frombuffer(seed, np.uint8))
+        rc = L.orc_prove(self._h, _p(_u8(advice)), _p(_u8(instance)), _p(np.ascontiguousarray(instance_len, dtype=np.uint32)), _p(seed),
+                         ctypes.c_uint32(proof_index), _p(buf), ctypes.byref(ln))
+        if rc:
+            raise RuntimeError("oracle prover failed rc=%d (2 = InstanceTooLarge, 3 = ConstraintSystemFailure)" % rc)
+        return buf[: ln.value].tobytes()
+
+    def verify(self, instance, instance_len, proof):
+        pb = _u8(np.frombuffer(proof, np.uint8))
+        return lib().orc_verify(self._h, _p(_u8(instance)), _p(np.ascontiguousarray(instance_len, dtype=np.uint32)), _p(pb), ctypes.c_size_t(pb.size))
+
+    def commitments(self):
+        kd = self.keydata
+        f = np.zeros((max(1, kd.cs.num_fixed), 64), np.uint8)
+        s = np.zeros((max(1, len(kd.cs.perm_columns)), 64), np.uint8)
+        lib().orc_key_commitments(self._h, _p(f), _p(s))
+        return f[: kd.cs.num_fixed], s[: len(kd.cs.perm_columns)]
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().orc_key_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def rnd(seed, proof, tag, idx):
+    out = np.zeros(32, np.uint8)
+    lib().orc_rnd(_p(_u8(np.frombuffer(seed, np.uint8))), ctypes.c_uint32(proof), ctypes.c_uint32(tag), ctypes.c_uint32(idx), _p(out))
+    return int.from_bytes(out.tobytes(), "little")
+
+
+def blake2b(data, personal16):
+    out = np.zeros(64, np.uint8)
+    d = _u8(np.frombuffer(data, np.uint8)) if len(data) else np.zeros(1, np.uint8)
+    lib().orc_blake2b(_p(d), ctypes.c_size_t(len(data)), ctypes.c_char_p(personal16), _p(out))
+    return out.tobytes()
+
+
+def synthetic_srs(k, seed=1):
+    """A structurally valid SRS for small test circuits: g[i] = [s_i] G with known s_i (insecure, test only),
+    g_lagrange = group inverse-DFT of g (as in params_15), w, u random multiples."""
+    from . import pasta as o
+    import random
+    rnd_ = random.Random(seed)
+    n = 1 << k
+    s = [rnd_.randrange(1, o.P) for _ in range(n)]
+    sl = o.intt(s, o.omega(k))
+    G = ints_to_bytes(list(o.VESTA_GEN)).reshape(64)
+    g = np.stack([point_mul(VESTA, G, ints_to_bytes([v])[0]) for v in s])
+    gl = np.stack([point_mul(VESTA, G, ints_to_bytes([v])[0]) for v in sl])
+    w = point_mul(VESTA, G, ints_to_bytes([rnd_.randrange(1, o.P)])[0])
+    u = point_mul(VESTA, G, ints_to_bytes([rnd_.randrange(1, o.P)])[0])
+    return {"k": k, "n": n, "g": g, "g_lagrange": gl, "w": w, "u": u}

@@ -129,7 +129,7 @@ void ntt_run(Ctx* ctx, int logn, bool inverse, const F* in, F* out, F* scratch, 
   TB_REQUIRE(batch >= 1 && batch <= 65535, "NTT batch out of range");
   static bool attr_set[2] = {false, false};
   if (!attr_set[F::params_id()]) {
-    TB_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    TB_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set[F::params_id()] = true;
   }
   NttArgs<F> a;
