@@ -101,6 +101,29 @@ void tb_srs_free(tb_srs* srs);
 tb_status tb_srs_commit(tb_ctx* ctx, const tb_srs* srs, int lagrange, uint32_t batch, const uint8_t* scalars, const uint8_t* blinds,
                         uint8_t* out_points);
 
+/* ---- proving key + batched prover: the drop-in for the body of Proof::create (taiga_halo2/src/proof.rs:25-42).
+ * tb_circuit_load replaces halo2_proofs keygen_pk's table building (COMPLIANCE_PROVING_KEY, constant.rs:145-152):
+ *   fixed_values : num_fixed columns x 2^k field elements (pk.fixed_values, Lagrange basis), column-major
+ *   sigma_values : num_perm_columns x 2^k field elements (pk.permutation.permutations, Lagrange basis)
+ * and builds coefficient forms, extended cosets (sub-coset major), l0/l_last/l_blind and the expression programs on
+ * the device.  tb_prove_batch replaces plonk::create_proof for n_proofs independent instances of that circuit:
+ *   advice       : n_proofs x num_advice x 2^k field elements (the table `synthesize` produced, after
+ *                  batch_invert_assigned; the last blinding_factors+1 rows are overwritten with blinding scalars)
+ *   instance     : per proof the instance columns concatenated (sum(instance_len) elements); instance_len[num_instance]
+ *   seed         : 32 bytes drawn from the caller's RNG (proof.rs:30); blinding scalars of proof i are derived from
+ *                  (seed, first_proof_index + i), so results are reproducible for a given seed
+ *   proofs_out   : n_proofs records of tb_pk_proof_len(pk) bytes at distance proof_stride
+ * Errors: TB_ERR_CONSTRAINT mirrors plonk::Error::ConstraintSystemFailure (lookup input missing from its table),
+ * TB_ERR_INVALID covers InstanceTooLarge and malformed arguments. */
+typedef struct tb_pk tb_pk;
+tb_status tb_circuit_load(tb_ctx* ctx, const tb_srs* srs, const tb_cs_desc* cs, const uint8_t* fixed_values, const uint8_t* sigma_values,
+                          tb_pk** out);
+void tb_pk_free(tb_pk* pk);
+size_t tb_pk_proof_len(const tb_pk* pk);
+tb_status tb_prove_batch(tb_ctx* ctx, const tb_pk* pk, uint32_t n_proofs, const uint8_t* advice, const uint8_t* instance,
+                         const uint32_t* instance_len, const uint8_t seed[32], uint32_t first_proof_index, uint8_t* proofs_out,
+                         size_t proof_stride);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,634 @@
+// Batched PLONKish / IPA prover: host orchestration of the sm_100a kernels for B independent proofs of one circuit.
+//
+// Drop-in for the body of `Proof::create` (taiga_halo2/src/proof.rs:25-42), i.e. halo2_proofs
+// `plonk::create_proof` + `poly::multiopen::create_proof` + `poly::commitment::create_proof` (EXT),
+// after the Rust side has run `synthesize` and handed over the advice table.  Everything between the upload of the
+// advice table and the download of the proof bytes stays on the device: commitments (fixed-base Pippenger), NTTs,
+// lookup sort, grand products, quotient evaluation tiled by sub-coset, multiopen, the 15 IPA rounds and the
+// Fiat-Shamir transcript.  Proof bytes are bit-identical to oracle/plonk.cpp for the same seed.
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <set>
+#include "capi_internal.cuh"
+#include "prover_kernels.cuh"
+
+namespace tb {
+
+enum PolyKind { PK_INST = 0, PK_ADV, PK_PZ, PK_LZ, PK_LPIN, PK_LPTAB, PK_FIXED, PK_SIG, PK_H, PK_RANDOM };
+struct PolyId { int kind, idx; bool operator<(const PolyId& o) const { return kind != o.kind ? kind < o.kind : idx < o.idx; } bool operator==(const PolyId& o) const { return kind == o.kind && idx == o.idx; } };
+struct QueryRef { PolyId poly; int rot; };
+
+struct Circuit {
+  Ctx* ctx; const Srs* srs;
+  // deep copy of the description
+  uint32_t k, na, nf, ni, degree, bf, P, L, chunk, nsets, pieces; int ext_k, R; size_t n, usable;
+  std::vector<tb_query> aq, fq, iq; std::vector<tb_column> perm;
+  std::vector<tb_expr_node> nodes; std::vector<uint32_t> roots; std::vector<uint8_t> consts_bytes; uint32_t nconsts;
+  std::vector<std::vector<uint32_t>> lk_in, lk_tab; std::vector<tb_lookup> lk_desc;
+  Fp vk_repr;  // canonical
+  // device tables
+  Fp *fixed_vals = nullptr, *fixed_polys = nullptr, *fixed_cosets = nullptr, *sig_vals = nullptr, *sig_polys = nullptr, *sig_cosets = nullptr;
+  Fp *l0 = nullptr, *l_last = nullptr, *l_blind = nullptr, *consts = nullptr, *wr_inv = nullptr;
+  int2 *d_aq = nullptr, *d_fq = nullptr, *d_iq = nullptr, *d_perm = nullptr;
+  QProgram prog_gates, prog_lookups;
+  std::vector<Fp> t_inv; Fp delta, zeta, omega, r_inv;
+  Fp delta_c0[16];
+  // evaluation / multiopen structure (host)
+  std::vector<QueryRef> evals;            // transcript order of the evaluation section
+  std::vector<QueryRef> queries;          // multiopen query order
+  std::vector<int> rots;                  // distinct rotations (evaluation points), in order of first appearance in `queries`
+  std::vector<PolyId> uniq; std::vector<int> uniq_set; std::vector<std::vector<int>> point_sets;
+  uint32_t proof_len;
+
+  ~Circuit() {
+    for (void* p : {(void*)fixed_vals, (void*)fixed_polys, (void*)fixed_cosets, (void*)sig_vals, (void*)sig_polys, (void*)sig_cosets, (void*)l0, (void*)l_last,
+                    (void*)l_blind, (void*)consts, (void*)wr_inv, (void*)d_aq, (void*)d_fq, (void*)d_iq, (void*)d_perm, (void*)prog_gates.dev, (void*)prog_lookups.dev})
+      if (p) cudaFree(p);
+  }
+};
+
+template <class T> static T* dev_upload(const std::vector<T>& v) {
+  T* p = nullptr;
+  TB_CUDA(cudaMalloc(&p, std::max<size_t>(1, v.size()) * sizeof(T)));
+  if (!v.empty()) TB_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return p;
+}
+static Fp* dev_alloc_fp(size_t count) { Fp* p = nullptr; TB_CUDA(cudaMalloc(&p, std::max<size_t>(1, count) * sizeof(Fp))); return p; }
+
+static NttHook<Fp> coset_hook(const Circuit& C, int k1, bool inverse) {
+  NttHook<Fp> h; h.use_const = 0; h.mod_bits = C.ext_k; h.k = (uint32_t)k1;
+  if (!inverse) { h.use_zeta = 1; h.z1 = C.zeta; h.z2 = C.zeta.sqr(); } else { h.use_zeta = 0; h.z1 = Fp::one(); h.z2 = Fp::one(); }
+  return h;
+}
+// polys [count][n] -> cosets [count][R][n] (sub-coset major)
+static void to_cosets(const Circuit& C, const Fp* polys, Fp* cosets, Fp* scratch, int count) {
+  if (!count) return;
+  for (int k1 = 0; k1 < C.R; ++k1) {
+    NttHook<Fp> h = coset_hook(C, k1, false);
+    ntt_run<Fp>(C.ctx, (int)C.k, false, polys, cosets + (size_t)k1 * C.n, scratch, count, (long long)C.n, (long long)C.R * C.n, &h, nullptr);
+  }
+}
+
+static Circuit* circuit_load(Ctx* ctx, const Srs* srs, const tb_cs_desc* cs, const uint8_t* fixed, const uint8_t* sigma) {
+  TB_REQUIRE(cs->k == srs->k, "circuit k must match the SRS");
+  TB_REQUIRE(cs->cs_degree >= 3 && cs->num_perm_columns <= 16 * (cs->cs_degree - 2), "unsupported constraint system shape");
+  std::unique_ptr<Circuit> Cp(new Circuit());
+  Circuit& C = *Cp;
+  C.ctx = ctx; C.srs = srs;
+  C.k = cs->k; C.n = size_t(1) << C.k; C.na = cs->num_advice; C.nf = cs->num_fixed; C.ni = cs->num_instance; C.degree = cs->cs_degree; C.bf = cs->blinding_factors;
+  TB_REQUIRE(C.n > C.bf + 2, "too few rows");
+  C.usable = C.n - (C.bf + 1);
+  C.P = cs->num_perm_columns; C.L = cs->num_lookups; C.chunk = C.degree - 2; C.nsets = C.P ? (C.P + C.chunk - 1) / C.chunk : 0;
+  C.pieces = C.degree - 1;
+  C.ext_k = C.k; while ((size_t(1) << C.ext_k) < C.n * C.pieces) C.ext_k++;
+  TB_REQUIRE(C.ext_k <= TW_LOG, "extended domain too large");
+  C.R = 1 << (C.ext_k - C.k);
+  C.aq.assign(cs->advice_queries, cs->advice_queries + cs->num_advice_queries);
+  C.fq.assign(cs->fixed_queries, cs->fixed_queries + cs->num_fixed_queries);
+  C.iq.assign(cs->instance_queries, cs->instance_queries + cs->num_instance_queries);
+  C.perm.assign(cs->perm_columns, cs->perm_columns + C.P);
+  C.nodes.assign(cs->nodes, cs->nodes + cs->num_nodes);
+  C.roots.assign(cs->constraint_roots, cs->constraint_roots + cs->num_constraints);
+  C.nconsts = cs->num_constants;
+  C.consts_bytes.assign(cs->constants, cs->constants + 32 * (size_t)cs->num_constants);
+  for (uint32_t l = 0; l < C.L; ++l) {
+    C.lk_in.emplace_back(cs->lookups[l].input_roots, cs->lookups[l].input_roots + cs->lookups[l].num_exprs);
+    C.lk_tab.emplace_back(cs->lookups[l].table_roots, cs->lookups[l].table_roots + cs->lookups[l].num_exprs);
+  }
+  for (auto& q : C.aq) TB_REQUIRE(q.column < C.na, "advice query column out of range");
+  for (auto& q : C.fq) TB_REQUIRE(q.column < C.nf, "fixed query column out of range");
+  for (auto& q : C.iq) TB_REQUIRE(q.column < C.ni, "instance query column out of range");
+  for (auto& nd : C.nodes) TB_REQUIRE(nd.op <= TB_EX_SCALE, "bad expression node");
+  memcpy(C.vk_repr.l, cs->vk_transcript_repr, 32);
+
+  C.delta = delta_const<Fp>(); C.zeta = zeta_const<Fp>(); C.omega = omega_k<Fp>((int)C.k);
+  C.r_inv = Fp::from_u32((uint32_t)C.R).inv();
+  for (uint32_t s = 0; s < 16; ++s) C.delta_c0[s] = C.delta.pow_u64((uint64_t)s * C.chunk);
+  Fp w_ext = omega_k<Fp>(C.ext_k);
+  { Fp zn = C.zeta.pow_u64(C.n), step = w_ext.pow_u64(C.n), cur = zn;
+    for (int k1 = 0; k1 < C.R; ++k1) { C.t_inv.push_back((cur - Fp::one()).inv()); cur = cur * step; }
+    std::vector<Fp> wr(C.R); Fp wri = step.inv(); wr[0] = Fp::one(); for (int e = 1; e < C.R; ++e) wr[e] = wr[e - 1] * wri;
+    C.wr_inv = dev_upload(wr); }
+
+  size_t n = C.n;
+  // constants -> Montgomery
+  { std::vector<Fp> cm(C.nconsts);
+    for (uint32_t i = 0; i < C.nconsts; ++i) { Fp v; memcpy(v.l, C.consts_bytes.data() + 32 * i, 32); cm[i] = v.to_mont(); }
+    C.consts = dev_upload(cm); }
+  auto q2 = [](const std::vector<tb_query>& qs) { std::vector<int2> v; for (auto& q : qs) v.push_back(make_int2((int)q.column, q.rotation)); return v; };
+  C.d_aq = dev_upload(q2(C.aq)); C.d_fq = dev_upload(q2(C.fq)); C.d_iq = dev_upload(q2(C.iq));
+  { std::vector<int2> pc; for (auto& c : C.perm) pc.push_back(make_int2((int)c.kind, (int)c.index)); C.d_perm = dev_upload(pc); }
+
+  DevBuf<Fp> scratch(ctx, std::max<size_t>(3, std::max<size_t>(C.nf, C.P)) * n);
+  auto load_cols = [&](const uint8_t* src, size_t cnt, Fp*& vals, Fp*& polys, Fp*& cosets) {
+    vals = dev_alloc_fp(cnt * n); polys = dev_alloc_fp(cnt * n); cosets = dev_alloc_fp(cnt * C.R * n);
+    if (!cnt) return;
+    TB_CUDA(cudaMemcpyAsync(vals, src, cnt * n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    fe_to_mont<Fp>(ctx, vals, cnt * n);
+    ntt_run<Fp>(ctx, (int)C.k, true, vals, polys, scratch.get(), (int)cnt, (long long)n, (long long)n, nullptr, nullptr);
+    to_cosets(C, polys, cosets, scratch.get(), (int)cnt);
+  };
+  load_cols(fixed, C.nf, C.fixed_vals, C.fixed_polys, C.fixed_cosets);
+  load_cols(sigma, C.P, C.sig_vals, C.sig_polys, C.sig_cosets);
+  // l0, l_last, l_blind
+  { std::vector<Fp> lag(3 * n, Fp::zero());
+    lag[0] = Fp::one(); lag[n + (n - C.bf - 1)] = Fp::one();
+    for (size_t r = n - C.bf; r < n; ++r) lag[2 * n + r] = Fp::one();
+    DevBuf<Fp> lv(ctx, 3 * n), lp(ctx, 3 * n), lc(ctx, 3 * (size_t)C.R * n);
+    lv.upload(lag.data(), 3 * n);
+    ntt_run<Fp>(ctx, (int)C.k, true, lv.get(), lp.get(), scratch.get(), 3, (long long)n, (long long)n, nullptr, nullptr);
+    to_cosets(C, lp.get(), lc.get(), scratch.get(), 3);
+    C.l0 = dev_alloc_fp((size_t)C.R * n); C.l_last = dev_alloc_fp((size_t)C.R * n); C.l_blind = dev_alloc_fp((size_t)C.R * n);
+    size_t sz = (size_t)C.R * n * sizeof(Fp);
+    TB_CUDA(cudaMemcpyAsync(C.l0, lc.get(), sz, cudaMemcpyDeviceToDevice, ctx->stream));
+    TB_CUDA(cudaMemcpyAsync(C.l_last, lc.get() + (size_t)C.R * n, sz, cudaMemcpyDeviceToDevice, ctx->stream));
+    TB_CUDA(cudaMemcpyAsync(C.l_blind, lc.get() + 2 * (size_t)C.R * n, sz, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->sync(); }
+
+  // expression programs (descriptor rebuilt from the deep copy so pointers stay valid)
+  { tb_cs_desc d = *cs;
+    q_compile_gates(&d, &C.prog_gates);
+    q_compile_lookups(&d, &C.prog_lookups); }
+
+  // ---- evaluation section order (plonk/prover.rs) and multiopen query order
+  int last_rot = -(int)(C.bf + 1);
+  for (auto& q : C.iq) C.evals.push_back({{PK_INST, (int)q.column}, q.rotation});
+  for (auto& q : C.aq) C.evals.push_back({{PK_ADV, (int)q.column}, q.rotation});
+  for (auto& q : C.fq) C.evals.push_back({{PK_FIXED, (int)q.column}, q.rotation});
+  C.evals.push_back({{PK_RANDOM, 0}, 0});
+  for (uint32_t c = 0; c < C.P; ++c) C.evals.push_back({{PK_SIG, (int)c}, 0});
+  for (uint32_t s = 0; s < C.nsets; ++s) {
+    C.evals.push_back({{PK_PZ, (int)s}, 0}); C.evals.push_back({{PK_PZ, (int)s}, 1});
+    if (s + 1 < C.nsets) C.evals.push_back({{PK_PZ, (int)s}, last_rot});
+  }
+  for (uint32_t l = 0; l < C.L; ++l) {
+    C.evals.push_back({{PK_LZ, (int)l}, 0}); C.evals.push_back({{PK_LZ, (int)l}, 1}); C.evals.push_back({{PK_LPIN, (int)l}, 0});
+    C.evals.push_back({{PK_LPIN, (int)l}, -1}); C.evals.push_back({{PK_LPTAB, (int)l}, 0});
+  }
+  for (auto& q : C.iq) C.queries.push_back({{PK_INST, (int)q.column}, q.rotation});
+  for (auto& q : C.aq) C.queries.push_back({{PK_ADV, (int)q.column}, q.rotation});
+  for (uint32_t s = 0; s < C.nsets; ++s) { C.queries.push_back({{PK_PZ, (int)s}, 0}); C.queries.push_back({{PK_PZ, (int)s}, 1}); }
+  for (int s = (int)C.nsets - 1; s >= 0; --s) if (s + 1 < (int)C.nsets) C.queries.push_back({{PK_PZ, s}, last_rot});
+  for (uint32_t l = 0; l < C.L; ++l) {
+    C.queries.push_back({{PK_LZ, (int)l}, 0}); C.queries.push_back({{PK_LPIN, (int)l}, 0}); C.queries.push_back({{PK_LPTAB, (int)l}, 0});
+    C.queries.push_back({{PK_LPIN, (int)l}, -1}); C.queries.push_back({{PK_LZ, (int)l}, 1});
+  }
+  for (auto& q : C.fq) C.queries.push_back({{PK_FIXED, (int)q.column}, q.rotation});
+  for (uint32_t c = 0; c < C.P; ++c) C.queries.push_back({{PK_SIG, (int)c}, 0});
+  C.queries.push_back({{PK_H, 0}, 0});
+  C.queries.push_back({{PK_RANDOM, 0}, 0});
+  // multiopen::construct_intermediate_sets (points identified by rotation; sets ordered by first appearance)
+  { std::map<int, int> point_index; std::vector<std::set<int>> prots;
+    for (auto& q : C.queries) {
+      if (!point_index.count(q.rot)) { int idx = (int)point_index.size(); point_index[q.rot] = idx; C.rots.push_back(q.rot); }
+      size_t pos = 0; for (; pos < C.uniq.size(); ++pos) if (C.uniq[pos] == q.poly) break;
+      if (pos == C.uniq.size()) { C.uniq.push_back(q.poly); prots.emplace_back(); }
+      prots[pos].insert(point_index[q.rot]);
+    }
+    std::map<std::set<int>, int> set_index;
+    for (size_t c = 0; c < C.uniq.size(); ++c) {
+      if (!set_index.count(prots[c])) { int idx = (int)set_index.size(); set_index[prots[c]] = idx; }
+      C.uniq_set.push_back(set_index[prots[c]]);
+    }
+    C.point_sets.resize(set_index.size());
+    for (auto& kv : set_index) for (int pi : kv.first) C.point_sets[kv.second].push_back(C.rots[pi]); }
+  for (auto& e : C.evals) if (std::find(C.rots.begin(), C.rots.end(), e.rot) == C.rots.end()) C.rots.push_back(e.rot);
+  uint32_t commits = C.na + 3 * C.L + C.nsets + 1 + C.pieces;
+  C.proof_len = 32 * (commits + (uint32_t)C.evals.size() + 1 + (uint32_t)C.point_sets.size() + 1 + 2 * C.k + 2);
+  return Cp.release();
+}
+
+// ---------------------------------------------------------------- IPA folding kernels
+__global__ void ipa_fold_g_kernel(Aff<Fq>* g, long long stride, int half, const Fp* vars, long long vstride, int u_slot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= half) return;
+  Aff<Fq>* gb = g + (long long)b * stride;
+  Fp u = vars[(long long)b * vstride + u_slot].from_mont();
+  Xyzz<Fq> acc = scalar_mul(gb[i + half], u.l);
+  acc.add_affine(gb[i]);
+  gb[i] = acc.to_affine();
+}
+__global__ void ipa_fold_scalars_kernel(Fp* p, Fp* bv, long long stride, int half, const Fp* vars, long long vstride, int u_slot, int uinv_slot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= half) return;
+  Fp u = vars[(long long)b * vstride + u_slot], ui = vars[(long long)b * vstride + uinv_slot];
+  Fp* pb = p + (long long)b * stride; Fp* bb = bv + (long long)b * stride;
+  st_fe(pb + i, ld_fe(pb + i) + ld_fe(pb + i + half) * ui);
+  st_fe(bb + i, ld_fe(bb + i) + ld_fe(bb + i + half) * u);
+}
+__global__ void fill_rows_const_kernel(Fp* v, long long stride, int row0, int count, Fp val, int B) {
+  int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= B * count) return;
+  v[(long long)(id / count) * stride + row0 + id % count] = val;
+}
+__global__ void gather_vars_kernel(Fp* out, long long ostride, const Fp* vars, long long vstride, const int* slots, int count, int B) {
+  int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= B * count) return;
+  int b = id / count, i = id % count;
+  out[(long long)b * ostride + i] = vars[(long long)b * vstride + slots[i]];
+}
+
+// ---------------------------------------------------------------- the prover
+struct VarAlloc {
+  int next = 0;
+  int one(int cnt = 1) { int r = next; next += cnt; return r; }
+};
+struct Prog {
+  std::vector<ScalarInstr> ins;
+  void op(int o, int dst, int a = 0, int b = 0, uint32_t imm = 0) { ScalarInstr i; i.op = (uint16_t)o; i.dst = (uint16_t)dst; i.a = (uint16_t)a; i.b = (uint16_t)b; i.imm = imm; ins.push_back(i); }
+};
+
+static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice_host, const uint8_t* instance_host, const uint32_t* instance_len,
+                        const uint8_t* seed, uint32_t proof0, uint8_t* proofs_out, size_t proof_stride) {
+  const Srs& srs = *C.srs;
+  const size_t n = C.n; const int k = (int)C.k; const int na = C.na, ni = C.ni, L = C.L, nsets = C.nsets, P = C.P, bf = C.bf;
+  const int ni1 = std::max(1, ni), L1 = std::max(1, L), ns1 = std::max(1, nsets);
+  cudaStream_t st = ctx->stream;
+  size_t inst_total = 0;
+  for (int c = 0; c < ni; ++c) { TB_REQUIRE(instance_len[c] <= C.usable, "InstanceTooLarge"); inst_total += instance_len[c]; }
+
+  // ---- per-proof scalar variables
+  VarAlloc va;
+  const int V_ONE = va.one(), V_THETA = va.one(), V_BETA = va.one(), V_GAMMA = va.one(), V_Y = va.one(), V_X = va.one(), V_XN = va.one();
+  const int V_X1 = va.one(), V_X2 = va.one(), V_X3 = va.one(), V_X4 = va.one(), V_XI = va.one(), V_Z = va.one();
+  const int V_PT = va.one((int)C.rots.size());
+  const int V_ADV_BLIND = va.one(na), V_LPIN_BLIND = va.one(L1), V_LPTAB_BLIND = va.one(L1), V_PZ_BLIND = va.one(ns1), V_LZ_BLIND = va.one(L1);
+  const int V_RANDOM_BLIND = va.one(), V_H_BLINDS = va.one(C.pieces), V_H_BLIND = va.one(), V_QPRIME_BLIND = va.one();
+  const int nps = (int)C.point_sets.size();
+  const int V_QBLIND = va.one(nps), V_P_BLIND = va.one(), V_S_BLIND = va.one(), V_F = va.one();
+  const int V_S_AT = va.one(), V_V = va.one(), V_LR = va.one(), V_RR = va.one(), V_VL = va.one(), V_VR = va.one(), V_VLZ = va.one(), V_VRZ = va.one();
+  const int V_U = va.one(), V_UINV = va.one(), V_T0 = va.one(), V_C = va.one();
+  const int NV = va.next;
+  DevBuf<Fp> vars(ctx, (size_t)B * NV);
+  vars.zero();
+  std::vector<Fp> hconsts = {Fp::one(), C.omega, C.omega.inv()};
+  DevBuf<Fp> dconsts(ctx, hconsts.size()); dconsts.upload(hconsts.data(), hconsts.size());
+  DevBuf<ScalarInstr> dprog(ctx, 4096);
+  auto run_prog = [&](Prog& p) {
+    if (p.ins.empty()) return;
+    TB_REQUIRE(p.ins.size() <= 4096, "scalar program too long");
+    // stream-ordered upload from a host vector that dies at scope end: stage through a pinned-free synchronous copy
+    TB_CUDA(cudaMemcpyAsync(dprog.get(), p.ins.data(), p.ins.size() * sizeof(ScalarInstr), cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    scalar_program(ctx, vars.get(), NV, dprog.get(), (int)p.ins.size(), dconsts.get(), B);
+    p.ins.clear();
+  };
+  { Prog p; p.op(S_CONST, V_ONE, 0, 0, 0); run_prog(p); }
+  auto VP = [&](int slot) { return vars.get() + slot; };  // pointer to slot of proof 0, stride NV
+
+  Transcripts tr; tr.init(ctx, B, C.proof_len, C.vk_repr);
+  DevBuf<Fp> scratch(ctx, (size_t)B * std::max({na, ni1, L1 * 3, ns1, (int)C.pieces, 4}) * n);
+  DevBuf<Aff<Fq>> pts(ctx, (size_t)B * std::max({na, ni1, 2 * L1, ns1, (int)C.pieces, 2}));
+
+  // ---- instance columns: pad, commit_lagrange(Blind::default() = 1) -> common_point, iNTT
+  DevBuf<Fp> inst_vals(ctx, (size_t)B * ni1 * n), inst_polys(ctx, (size_t)B * ni1 * n);
+  inst_vals.zero();
+  if (ni) {
+    size_t off = 0;
+    for (int c = 0; c < ni; ++c) {
+      if (instance_len[c])
+        TB_CUDA(cudaMemcpy2DAsync(inst_vals.get() + (size_t)c * n, (size_t)ni * n * 32, instance_host + 32 * off, inst_total * 32, (size_t)instance_len[c] * 32, B,
+                                  cudaMemcpyHostToDevice, st));
+      off += instance_len[c];
+    }
+    fe_to_mont<Fp>(ctx, inst_vals.get(), (size_t)B * ni * n);
+    DevBuf<Fp> ones(ctx, (size_t)B * ni);
+    fill_rows_const_kernel<<<(B * ni + 63) / 64, 64, 0, st>>>(ones.get(), ni, 0, ni, Fp::one(), B);
+    srs.commit(ctx, true, inst_vals.get(), (long long)n, B * ni, ones.get(), pts.get());
+    tr.points(pts.get(), ni, ni, false);
+    ntt_run<Fp>(ctx, k, true, inst_vals.get(), inst_polys.get(), scratch.get(), B * ni, (long long)n, (long long)n, nullptr, nullptr);
+  }
+  // ---- advice columns: upload, blinding rows, commit, iNTT
+  DevBuf<Fp> adv_vals(ctx, (size_t)B * na * n), adv_polys(ctx, (size_t)B * na * n);
+  TB_CUDA(cudaMemcpyAsync(adv_vals.get(), advice_host, (size_t)B * na * n * 32, cudaMemcpyHostToDevice, st));
+  fe_to_mont<Fp>(ctx, adv_vals.get(), (size_t)B * na * n);
+  for (int c = 0; c < na; ++c)
+    prf_fill(ctx, seed, proof0, R_ADVICE_ROWS, (uint32_t)(c * (bf + 1)), adv_vals.get() + (size_t)c * n + C.usable, (long long)na * n, 1, bf + 1, B);
+  prf_fill(ctx, seed, proof0, R_ADVICE_BLIND, 0, VP(V_ADV_BLIND), NV, 1, na, B);
+  { DevBuf<Fp> blinds(ctx, (size_t)B * na);
+    poly_copy(ctx, blinds.get(), na, VP(V_ADV_BLIND), NV, na, B);
+    srs.commit(ctx, true, adv_vals.get(), (long long)n, B * na, blinds.get(), pts.get()); }
+  tr.points(pts.get(), na, na, true);
+  ntt_run<Fp>(ctx, k, true, adv_vals.get(), adv_polys.get(), scratch.get(), B * na, (long long)n, (long long)n, nullptr, nullptr);
+  tr.squeeze(VP(V_THETA), NV, 1);
+
+  // ---- lookups: compress (Lagrange domain), sort, arrange, blind, commit A', S'
+  DevBuf<Fp> lkA(ctx, (size_t)B * L1 * n), lkS(ctx, (size_t)B * L1 * n), lpin(ctx, (size_t)B * L1 * n), lptab(ctx, (size_t)B * L1 * n);
+  DevBuf<Fp> lpin_polys(ctx, (size_t)B * L1 * n), lptab_polys(ctx, (size_t)B * L1 * n);
+  QData qd; memset(&qd, 0, sizeof(qd));
+  qd.aq = C.d_aq; qd.fq = C.d_fq; qd.iq = C.d_iq; qd.consts = C.consts; qd.chal = vars.get(); qd.chal_stride = NV; qd.y_slot = V_Y; qd.theta_slot = V_THETA;
+  qd.n = (int)n; qd.lk_pstride = (long long)L1 * n;
+  if (L) {
+    qd.adv = adv_vals.get(); qd.adv_pstride = (long long)na * n; qd.inst = inst_vals.get(); qd.inst_pstride = (long long)ni1 * n;
+    qd.fix = C.fixed_vals; qd.R = 1; qd.k1 = 0; qd.gate_out = nullptr; qd.lkA = lkA.get(); qd.lkS = lkS.get();
+    q_run(ctx, C.prog_lookups, qd, B);
+    DevBuf<Fp> keysA(ctx, (size_t)B * L * n), keysS(ctx, (size_t)B * L * n), left(ctx, (size_t)B * L * n);
+    DevBuf<uint32_t> derr(ctx, 1); derr.zero();
+    lookup_keys(ctx, keysA.get(), lkA.get(), (int)n, (int)C.usable, B * L);
+    lookup_keys(ctx, keysS.get(), lkS.get(), (int)n, (int)C.usable, B * L);
+    sort_keys(ctx, keysA.get(), (int)n, B * L);
+    sort_keys(ctx, keysS.get(), (int)n, B * L);
+    lookup_arrange(ctx, keysA.get(), keysS.get(), left.get(), lptab.get(), (int)n, (int)C.usable, B * L, derr.get());
+    uint32_t herr = 0; TB_CUDA(cudaMemcpyAsync(&herr, derr.get(), 4, cudaMemcpyDeviceToHost, st)); ctx->sync();
+    if (herr) throw ConstraintError("lookup input not contained in the table (ConstraintSystemFailure)");
+    TB_CUDA(cudaMemcpyAsync(lpin.get(), keysA.get(), (size_t)B * L * n * 32, cudaMemcpyDeviceToDevice, st));
+    fe_to_mont<Fp>(ctx, lpin.get(), (size_t)B * L * n);
+    fe_to_mont<Fp>(ctx, lptab.get(), (size_t)B * L * n);
+    for (int l = 0; l < L; ++l) {
+      prf_fill(ctx, seed, proof0, R_LK_IN_ROWS, (uint32_t)(l * (bf + 1)), lpin.get() + (size_t)l * n + C.usable, (long long)L * n, 1, bf + 1, B);
+      prf_fill(ctx, seed, proof0, R_LK_TAB_ROWS, (uint32_t)(l * (bf + 1)), lptab.get() + (size_t)l * n + C.usable, (long long)L * n, 1, bf + 1, B);
+    }
+    prf_fill(ctx, seed, proof0, R_LK_IN_BLIND, 0, VP(V_LPIN_BLIND), NV, 1, L, B);
+    prf_fill(ctx, seed, proof0, R_LK_TAB_BLIND, 0, VP(V_LPTAB_BLIND), NV, 1, L, B);
+    // commit in transcript order: per lookup A' then S'
+    DevBuf<Fp> blinds(ctx, (size_t)B * L);
+    DevBuf<Aff<Fq>> pa(ctx, (size_t)B * L), ps(ctx, (size_t)B * L);
+    poly_copy(ctx, blinds.get(), L, VP(V_LPIN_BLIND), NV, L, B);
+    srs.commit(ctx, true, lpin.get(), (long long)n, B * L, blinds.get(), pa.get());
+    poly_copy(ctx, blinds.get(), L, VP(V_LPTAB_BLIND), NV, L, B);
+    srs.commit(ctx, true, lptab.get(), (long long)n, B * L, blinds.get(), ps.get());
+    for (int l = 0; l < L; ++l) { tr.points(pa.get() + l, L, 1, true); tr.points(ps.get() + l, L, 1, true); }
+    ntt_run<Fp>(ctx, k, true, lpin.get(), lpin_polys.get(), scratch.get(), B * L, (long long)n, (long long)n, nullptr, nullptr);
+    ntt_run<Fp>(ctx, k, true, lptab.get(), lptab_polys.get(), scratch.get(), B * L, (long long)n, (long long)n, nullptr, nullptr);
+  }
+  tr.squeeze(VP(V_BETA), NV, 1);
+  tr.squeeze(VP(V_GAMMA), NV, 1);
+
+  // ---- permutation grand products
+  DevBuf<Fp> pz_polys(ctx, (size_t)B * ns1 * n);
+  if (nsets) {
+    DevBuf<Fp> num(ctx, (size_t)B * nsets * n), den(ctx, (size_t)B * nsets * n), z(ctx, (size_t)B * nsets * n);
+    PermFrac pf; memset(&pf, 0, sizeof(pf));
+    pf.adv = adv_vals.get(); pf.adv_pstride = (long long)na * n; pf.inst = inst_vals.get(); pf.inst_pstride = (long long)ni1 * n; pf.fix = C.fixed_vals;
+    pf.sig = C.sig_vals; pf.perm_cols = C.d_perm; pf.P = P; pf.chunk = C.chunk; pf.nsets = nsets; pf.chal = vars.get(); pf.chal_stride = NV;
+    pf.beta_slot = V_BETA; pf.gamma_slot = V_GAMMA; pf.delta = C.delta; pf.omega = C.omega; memcpy(pf.delta_c0, C.delta_c0, sizeof(pf.delta_c0));
+    pf.tw = ctx->tw_fp.fwd; pf.num = num.get(); pf.den = den.get(); pf.pstride = (long long)nsets * n; pf.n = (int)n; pf.k = k;
+    perm_fractions(ctx, pf, B);
+    batch_inverse(ctx, den.get(), (size_t)B * nsets * n);
+    vec_mul(ctx, num.get(), den.get(), (size_t)B * nsets * n);
+    prefix_product(ctx, z.get(), num.get(), (int)n, B * nsets);
+    perm_chain(ctx, z.get(), (long long)nsets * n, nsets, (int)n, (int)(n - bf - 1), B);
+    for (int s = 0; s < nsets; ++s)
+      prf_fill(ctx, seed, proof0, R_PERM_ROWS, (uint32_t)(s * bf), z.get() + (size_t)s * n + (n - bf), (long long)nsets * n, 1, bf, B);
+    prf_fill(ctx, seed, proof0, R_PERM_BLIND, 0, VP(V_PZ_BLIND), NV, 1, nsets, B);
+    DevBuf<Fp> blinds(ctx, (size_t)B * nsets);
+    poly_copy(ctx, blinds.get(), nsets, VP(V_PZ_BLIND), NV, nsets, B);
+    srs.commit(ctx, true, z.get(), (long long)n, B * nsets, blinds.get(), pts.get());
+    tr.points(pts.get(), nsets, nsets, true);
+    ntt_run<Fp>(ctx, k, true, z.get(), pz_polys.get(), scratch.get(), B * nsets, (long long)n, (long long)n, nullptr, nullptr);
+  }
+  // ---- lookup grand products
+  DevBuf<Fp> lz_polys(ctx, (size_t)B * L1 * n);
+  if (L) {
+    DevBuf<Fp> num(ctx, (size_t)B * L * n), den(ctx, (size_t)B * L * n), z(ctx, (size_t)B * L * n);
+    lookup_fractions(ctx, lkA.get(), lkS.get(), lpin.get(), lptab.get(), num.get(), den.get(), (long long)L * n, L, (int)n, vars.get(), NV, V_BETA, V_GAMMA, B);
+    batch_inverse(ctx, den.get(), (size_t)B * L * n);
+    vec_mul(ctx, num.get(), den.get(), (size_t)B * L * n);
+    prefix_product(ctx, z.get(), num.get(), (int)n, B * L);
+    for (int l = 0; l < L; ++l)
+      prf_fill(ctx, seed, proof0, R_LKZ_ROWS, (uint32_t)(l * bf), z.get() + (size_t)l * n + (n - bf), (long long)L * n, 1, bf, B);
+    prf_fill(ctx, seed, proof0, R_LKZ_BLIND, 0, VP(V_LZ_BLIND), NV, 1, L, B);
+    DevBuf<Fp> blinds(ctx, (size_t)B * L);
+    poly_copy(ctx, blinds.get(), L, VP(V_LZ_BLIND), NV, L, B);
+    srs.commit(ctx, true, z.get(), (long long)n, B * L, blinds.get(), pts.get());
+    tr.points(pts.get(), L, L, true);
+    ntt_run<Fp>(ctx, k, true, z.get(), lz_polys.get(), scratch.get(), B * L, (long long)n, (long long)n, nullptr, nullptr);
+  }
+  // ---- vanishing argument: random polynomial
+  DevBuf<Fp> random_poly(ctx, (size_t)B * n);
+  prf_fill(ctx, seed, proof0, R_RANDOM_POLY, 0, random_poly.get(), (long long)n, 1, (int)n, B);
+  prf_fill(ctx, seed, proof0, R_RANDOM_BLIND, 0, VP(V_RANDOM_BLIND), NV, 1, 1, B);
+  { DevBuf<Fp> blinds(ctx, B); poly_copy(ctx, blinds.get(), 1, VP(V_RANDOM_BLIND), NV, 1, B);
+    srs.commit(ctx, false, random_poly.get(), (long long)n, B, blinds.get(), pts.get()); }
+  tr.points(pts.get(), 1, 1, true);
+  tr.squeeze(VP(V_Y), NV, 1);
+
+  // ---- quotient, tiled by sub-coset
+  const int R = C.R;
+  DevBuf<Fp> hext(ctx, (size_t)B * R * n), hcoef(ctx, (size_t)B * C.pieces * n);
+  { DevBuf<Fp> c_adv(ctx, (size_t)B * na * n), c_inst(ctx, (size_t)B * ni1 * n), c_pz(ctx, (size_t)B * ns1 * n), c_lz(ctx, (size_t)B * L1 * n),
+        c_lpin(ctx, (size_t)B * L1 * n), c_lptab(ctx, (size_t)B * L1 * n), c_lkA(ctx, (size_t)B * L1 * n), c_lkS(ctx, (size_t)B * L1 * n), gate(ctx, (size_t)B * n);
+    for (int k1 = 0; k1 < R; ++k1) {
+      NttHook<Fp> h = coset_hook(C, k1, false);
+      ntt_run<Fp>(ctx, k, false, adv_polys.get(), c_adv.get(), scratch.get(), B * na, (long long)n, (long long)n, &h, nullptr);
+      if (ni) ntt_run<Fp>(ctx, k, false, inst_polys.get(), c_inst.get(), scratch.get(), B * ni, (long long)n, (long long)n, &h, nullptr);
+      if (nsets) ntt_run<Fp>(ctx, k, false, pz_polys.get(), c_pz.get(), scratch.get(), B * nsets, (long long)n, (long long)n, &h, nullptr);
+      if (L) {
+        ntt_run<Fp>(ctx, k, false, lz_polys.get(), c_lz.get(), scratch.get(), B * L, (long long)n, (long long)n, &h, nullptr);
+        ntt_run<Fp>(ctx, k, false, lpin_polys.get(), c_lpin.get(), scratch.get(), B * L, (long long)n, (long long)n, &h, nullptr);
+        ntt_run<Fp>(ctx, k, false, lptab_polys.get(), c_lptab.get(), scratch.get(), B * L, (long long)n, (long long)n, &h, nullptr);
+      }
+      qd.adv = c_adv.get(); qd.adv_pstride = (long long)na * n; qd.inst = c_inst.get(); qd.inst_pstride = (long long)ni1 * n;
+      qd.fix = C.fixed_cosets; qd.R = R; qd.k1 = k1; qd.lkA = c_lkA.get(); qd.lkS = c_lkS.get();
+      qd.gate_out = gate.get(); qd.gate_pstride = (long long)n;
+      q_run(ctx, C.prog_gates, qd, B);
+      if (L) { qd.gate_out = nullptr; q_run(ctx, C.prog_lookups, qd, B); }
+      QFinish f; memset(&f, 0, sizeof(f));
+      f.gate = gate.get(); f.adv = c_adv.get(); f.adv_pstride = (long long)na * n; f.inst = c_inst.get(); f.inst_pstride = (long long)ni1 * n;
+      f.fix = C.fixed_cosets; f.sig = C.sig_cosets; f.R = R; f.k1 = k1; f.l0 = C.l0; f.l_last = C.l_last; f.l_blind = C.l_blind;
+      f.pz = c_pz.get(); f.pz_pstride = (long long)ns1 * n; f.lz = c_lz.get(); f.lpin = c_lpin.get(); f.lptab = c_lptab.get(); f.lk_pstride = (long long)L1 * n;
+      f.lkA = c_lkA.get(); f.lkS = c_lkS.get(); f.perm_cols = C.d_perm; f.P = P; f.chunk = C.chunk; f.nsets = nsets; f.L = L; f.bf = bf;
+      f.chal = vars.get(); f.chal_stride = NV; f.y_slot = V_Y; f.beta_slot = V_BETA; f.gamma_slot = V_GAMMA;
+      f.delta = C.delta; f.zeta = C.zeta; f.t_inv = C.t_inv[k1]; memcpy(f.delta_c0, C.delta_c0, sizeof(f.delta_c0)); f.tw = ctx->tw_fp.fwd;
+      f.ext_k = C.ext_k; f.k = k; f.out = hext.get(); f.out_pstride = (long long)R * n; f.n = (int)n;
+      q_finish(ctx, f, B);
+    }
+    // extended_to_coeff: per sub-coset iNTT with w_ext^(-i*k1) (step A), then the size-R cross transform (step B)
+    DevBuf<Fp> V(ctx, (size_t)B * R * n);
+    for (int k1 = 0; k1 < R; ++k1) {
+      NttHook<Fp> h = coset_hook(C, k1, true);
+      ntt_run<Fp>(ctx, k, true, hext.get() + (size_t)k1 * n, V.get() + (size_t)k1 * n, scratch.get(), B, (long long)R * n, (long long)R * n, nullptr, &h);
+    }
+    h_cross(ctx, V.get(), (long long)R * n, hcoef.get(), (long long)C.pieces * n, (int)n, R, (int)C.pieces, C.wr_inv, C.r_inv, C.zeta.sqr(), B);
+  }
+  prf_fill(ctx, seed, proof0, R_H_BLIND, 0, VP(V_H_BLINDS), NV, 1, (int)C.pieces, B);
+  { DevBuf<Fp> blinds(ctx, (size_t)B * C.pieces);
+    poly_copy(ctx, blinds.get(), C.pieces, VP(V_H_BLINDS), NV, C.pieces, B);
+    srs.commit(ctx, false, hcoef.get(), (long long)n, B * (int)C.pieces, blinds.get(), pts.get()); }
+  tr.points(pts.get(), C.pieces, C.pieces, true);
+  tr.squeeze(VP(V_X), NV, 1);
+
+  // ---- evaluation points, h(X) = sum xn^i h_i, blinds
+  DevBuf<Fp> h_poly(ctx, (size_t)B * n);
+  { Prog p;
+    p.op(S_POW2K, V_XN, V_X, 0, (uint32_t)k);
+    for (size_t i = 0; i < C.rots.size(); ++i) {
+      int rot = C.rots[i], dst = V_PT + (int)i;
+      p.op(S_COPY, dst, V_X);
+      if (rot) { p.op(S_CONST, V_T0, 0, 0, rot > 0 ? 1 : 2); for (int r = 0; r < std::abs(rot); ++r) p.op(S_MUL, dst, dst, V_T0); }
+    }
+    p.op(S_SUB, V_H_BLIND, V_H_BLIND, V_H_BLIND);
+    for (int i = (int)C.pieces - 1; i >= 0; --i) p.op(S_FMA, V_H_BLIND, V_XN, V_H_BLINDS + i);
+    run_prog(p); }
+  TB_CUDA(cudaMemsetAsync(h_poly.get(), 0, (size_t)B * n * 32, st));
+  for (int i = (int)C.pieces - 1; i >= 0; --i) poly_fma(ctx, h_poly.get(), (long long)n, VP(V_XN), NV, hcoef.get() + (size_t)i * n, (long long)C.pieces * n, (int)n, B);
+
+  auto rot_slot = [&](int rot) { return V_PT + (int)(std::find(C.rots.begin(), C.rots.end(), rot) - C.rots.begin()); };
+  const long long nn = (long long)n;
+  auto mk_item = [](const Fp* base, long long bstride, int point) { EvalItem it; it.base = base; it.bstride = bstride; it.point = point; it.pad = 0; return it; };
+  struct PRef { const Fp* base; long long bstride; int blind_slot; };
+  auto poly_ref = [&](const PolyId& id) -> PRef {
+    switch (id.kind) {
+      case PK_INST: return {inst_polys.get() + (size_t)id.idx * n, (long long)ni1 * nn, V_ONE};
+      case PK_ADV: return {adv_polys.get() + (size_t)id.idx * n, (long long)na * nn, V_ADV_BLIND + id.idx};
+      case PK_PZ: return {pz_polys.get() + (size_t)id.idx * n, (long long)ns1 * nn, V_PZ_BLIND + id.idx};
+      case PK_LZ: return {lz_polys.get() + (size_t)id.idx * n, (long long)L1 * nn, V_LZ_BLIND + id.idx};
+      case PK_LPIN: return {lpin_polys.get() + (size_t)id.idx * n, (long long)L1 * nn, V_LPIN_BLIND + id.idx};
+      case PK_LPTAB: return {lptab_polys.get() + (size_t)id.idx * n, (long long)L1 * nn, V_LPTAB_BLIND + id.idx};
+      case PK_FIXED: return {C.fixed_polys + (size_t)id.idx * n, 0, V_ONE};
+      case PK_SIG: return {C.sig_polys + (size_t)id.idx * n, 0, V_ONE};
+      case PK_H: return {h_poly.get(), nn, V_H_BLIND};
+      default: return {random_poly.get(), nn, V_RANDOM_BLIND};
+    }
+  };
+  { std::vector<EvalItem> items;
+    for (auto& e : C.evals) { PRef r = poly_ref(e.poly); items.push_back(mk_item(r.base, r.bstride, rot_slot(e.rot))); }
+    DevBuf<EvalItem> ditems(ctx, items.size()); ditems.upload(items.data(), items.size()); ctx->sync();
+    DevBuf<Fp> ev(ctx, (size_t)B * items.size());
+    poly_eval(ctx, ditems.get(), (int)items.size(), vars.get(), NV, ev.get(), (long long)items.size(), (int)n, B);
+    tr.scalars(ev.get(), (long long)items.size(), (int)items.size(), true); }
+
+  // ---- multiopen
+  tr.squeeze(VP(V_X1), NV, 1);
+  tr.squeeze(VP(V_X2), NV, 1);
+  DevBuf<Fp> q_polys(ctx, (size_t)B * nps * n), q_prime(ctx, (size_t)B * n), kd_a(ctx, (size_t)B * n), kd_b(ctx, (size_t)B * n);
+  { std::vector<char> started(nps, 0); Prog p;
+    for (int s = 0; s < nps; ++s) p.op(S_SUB, V_QBLIND + s, V_QBLIND + s, V_QBLIND + s);
+    for (size_t c = 0; c < C.uniq.size(); ++c) {
+      PRef r = poly_ref(C.uniq[c]); int s = C.uniq_set[c];
+      Fp* q = q_polys.get() + (size_t)s * n;
+      if (!started[s]) { poly_copy(ctx, q, (long long)nps * n, r.base, r.bstride, (int)n, B); started[s] = 1; }
+      else poly_fma(ctx, q, (long long)nps * n, VP(V_X1), NV, r.base, r.bstride, (int)n, B);
+      p.op(S_FMA, V_QBLIND + s, V_X1, r.blind_slot);
+    }
+    run_prog(p); }
+  for (int s = 0; s < nps; ++s) {
+    const Fp* cur = q_polys.get() + (size_t)s * n; long long cur_stride = (long long)nps * n;
+    Fp* bufs[2] = {kd_a.get(), kd_b.get()}; int w = 0;
+    for (int rot : C.point_sets[s]) {
+      poly_kate_div(ctx, bufs[w], (long long)n, cur, cur_stride, VP(rot_slot(rot)), NV, (int)n, B);
+      cur = bufs[w]; cur_stride = (long long)n; w ^= 1;
+    }
+    if (s == 0) poly_copy(ctx, q_prime.get(), (long long)n, cur, cur_stride, (int)n, B);
+    else poly_fma(ctx, q_prime.get(), (long long)n, VP(V_X2), NV, cur, cur_stride, (int)n, B);
+  }
+  prf_fill(ctx, seed, proof0, R_QPRIME_BLIND, 0, VP(V_QPRIME_BLIND), NV, 1, 1, B);
+  { DevBuf<Fp> blinds(ctx, B); poly_copy(ctx, blinds.get(), 1, VP(V_QPRIME_BLIND), NV, 1, B);
+    srs.commit(ctx, false, q_prime.get(), (long long)n, B, blinds.get(), pts.get()); }
+  tr.points(pts.get(), 1, 1, true);
+  tr.squeeze(VP(V_X3), NV, 1);
+  { std::vector<EvalItem> items;
+    for (int s = 0; s < nps; ++s) items.push_back(mk_item(q_polys.get() + (size_t)s * n, (long long)nps * nn, V_X3));
+    DevBuf<EvalItem> ditems(ctx, items.size()); ditems.upload(items.data(), items.size()); ctx->sync();
+    DevBuf<Fp> ev(ctx, (size_t)B * nps);
+    poly_eval(ctx, ditems.get(), nps, vars.get(), NV, ev.get(), nps, (int)n, B);
+    tr.scalars(ev.get(), nps, nps, true); }
+  tr.squeeze(VP(V_X4), NV, 1);
+  // p(X) = ((q' x4 + q_0) x4 + q_1) ... ; same for the blinds
+  DevBuf<Fp> pprime(ctx, (size_t)B * n), bvec(ctx, (size_t)B * n), s_poly(ctx, (size_t)B * n);
+  Fp* p_poly = q_prime.get();
+  { Prog p; p.op(S_COPY, V_P_BLIND, V_QPRIME_BLIND);
+    for (int s = 0; s < nps; ++s) { poly_fma(ctx, p_poly, (long long)n, VP(V_X4), NV, q_polys.get() + (size_t)s * n, (long long)nps * n, (int)n, B); p.op(S_FMA, V_P_BLIND, V_X4, V_QBLIND + s); }
+    run_prog(p); }
+
+  // ---- inner product argument (poly/commitment/prover.rs)
+  prf_fill(ctx, seed, proof0, R_S_POLY, 0, s_poly.get(), (long long)n, 1, (int)n, B);
+  prf_fill(ctx, seed, proof0, R_S_BLIND, 0, VP(V_S_BLIND), NV, 1, 1, B);
+  DevBuf<EvalItem> one_item(ctx, 1);
+  auto eval_one = [&](const Fp* poly, int out_slot) {
+    EvalItem it = mk_item(poly, nn, V_X3);
+    one_item.upload(&it, 1); ctx->sync();
+    poly_eval(ctx, one_item.get(), 1, vars.get(), NV, VP(out_slot), NV, (int)n, B);
+  };
+  eval_one(s_poly.get(), V_S_AT);
+  poly_add_at(ctx, s_poly.get(), (long long)n, 0, VP(V_S_AT), NV, -1, B);
+  { DevBuf<Fp> blinds(ctx, B); poly_copy(ctx, blinds.get(), 1, VP(V_S_BLIND), NV, 1, B);
+    srs.commit(ctx, false, s_poly.get(), (long long)n, B, blinds.get(), pts.get()); }
+  tr.points(pts.get(), 1, 1, true);
+  tr.squeeze(VP(V_XI), NV, 1);
+  tr.squeeze(VP(V_Z), NV, 1);
+  poly_copy(ctx, pprime.get(), (long long)n, s_poly.get(), (long long)n, (int)n, B);
+  poly_fma(ctx, pprime.get(), (long long)n, VP(V_XI), NV, p_poly, (long long)n, (int)n, B);
+  eval_one(pprime.get(), V_V);
+  poly_add_at(ctx, pprime.get(), (long long)n, 0, VP(V_V), NV, -1, B);
+  { Prog p; p.op(S_MUL, V_F, V_S_BLIND, V_XI); p.op(S_ADD, V_F, V_F, V_P_BLIND); run_prog(p); }
+  powers(ctx, bvec.get(), (long long)n, VP(V_X3), NV, (int)n, B);
+  DevBuf<Aff<Fq>> gprime(ctx, (size_t)B * n);
+  TB_CUDA(cudaMemcpy2DAsync(gprime.get(), n * sizeof(Aff<Fq>), srs.g, 0, n * sizeof(Aff<Fq>), B, cudaMemcpyDeviceToDevice, st));
+  DevBuf<Xyzz<Fq>> accL(ctx, B), accR(ctx, B);
+  DevBuf<Aff<Fq>> ptL(ctx, B), ptR(ctx, B);
+  DevBuf<Fp> ex(ctx, (size_t)B * 2);
+  DevBuf<int> dslots(ctx, 4);
+  for (int j = 0; j < k; ++j) {
+    int half = (int)(n >> (j + 1));
+    MsmConfig cfg;
+    msm_run<Fq, Fp>(ctx, pprime.get() + half, (long long)n, gprime.get(), (long long)n, half, B, cfg, accL.get());
+    msm_run<Fq, Fp>(ctx, pprime.get(), (long long)n, gprime.get() + half, (long long)n, half, B, cfg, accR.get());
+    inner_product(ctx, VP(V_VL), NV, pprime.get() + half, (long long)n, bvec.get(), (long long)n, half, B);
+    inner_product(ctx, VP(V_VR), NV, pprime.get(), (long long)n, bvec.get() + half, (long long)n, half, B);
+    prf_fill(ctx, seed, proof0, R_IPA_L, (uint32_t)j, VP(V_LR), NV, 1, 1, B);
+    prf_fill(ctx, seed, proof0, R_IPA_R, (uint32_t)j, VP(V_RR), NV, 1, 1, B);
+    { Prog p; p.op(S_MUL, V_VLZ, V_VL, V_Z); p.op(S_MUL, V_VRZ, V_VR, V_Z); run_prog(p); }
+    // L = accL + lr * w + (vl z) * u   (srs.wu = {w, u})
+    int slotsL[2] = {V_LR, V_VLZ}, slotsR[2] = {V_RR, V_VRZ};
+    TB_CUDA(cudaMemcpyAsync(dslots.get(), slotsL, 8, cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaMemcpyAsync(dslots.get() + 2, slotsR, 8, cudaMemcpyHostToDevice, st));
+    ctx->sync();
+    gather_vars_kernel<<<(B * 2 + 63) / 64, 64, 0, st>>>(ex.get(), 2, vars.get(), NV, dslots.get(), 2, B);
+    points_finalize<Fq, Fp>(ctx, accL.get(), B, ex.get(), srs.wu, 2, ptL.get());
+    gather_vars_kernel<<<(B * 2 + 63) / 64, 64, 0, st>>>(ex.get(), 2, vars.get(), NV, dslots.get() + 2, 2, B);
+    points_finalize<Fq, Fp>(ctx, accR.get(), B, ex.get(), srs.wu, 2, ptR.get());
+    tr.points(ptL.get(), 1, 1, true);
+    tr.points(ptR.get(), 1, 1, true);
+    tr.squeeze(VP(V_U), NV, 1);
+    { Prog p; p.op(S_INV, V_UINV, V_U); p.op(S_MUL, V_T0, V_LR, V_UINV); p.op(S_ADD, V_F, V_F, V_T0); p.op(S_MUL, V_T0, V_RR, V_U); p.op(S_ADD, V_F, V_F, V_T0); run_prog(p); }
+    ipa_fold_g_kernel<<<dim3((half + 63) / 64, B), 64, 0, st>>>(gprime.get(), (long long)n, half, vars.get(), NV, V_U);
+    TB_LAUNCH_CHECK();
+    ipa_fold_scalars_kernel<<<dim3((half + 127) / 128, B), 128, 0, st>>>(pprime.get(), bvec.get(), (long long)n, half, vars.get(), NV, V_U, V_UINV);
+    TB_LAUNCH_CHECK(); ctx->launches += 4;
+  }
+  poly_copy(ctx, VP(V_C), NV, pprime.get(), (long long)n, 1, B);
+  tr.scalars(VP(V_C), NV, 1, true);
+  tr.scalars(VP(V_F), NV, 1, true);
+
+  // ---- download
+  std::vector<TrState> hst(B);
+  TB_CUDA(cudaMemcpyAsync(hst.data(), tr.states.get(), (size_t)B * sizeof(TrState), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpy2DAsync(proofs_out, proof_stride, tr.proofs.get(), C.proof_len, C.proof_len, B, cudaMemcpyDeviceToHost, st));
+  ctx->sync();
+  for (int b = 0; b < B; ++b) {
+    if (hst[b].error & TR_ERR_INFINITY) throw std::runtime_error("cannot write points at infinity to the transcript");
+    if (hst[b].error || hst[b].proof_len != C.proof_len) throw std::runtime_error("internal error: proof length mismatch");
+  }
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+tb_status tb_circuit_load(tb_ctx* ctx, const tb_srs* srs, const tb_cs_desc* cs, const uint8_t* fixed_values, const uint8_t* sigma_values, tb_pk** out) {
+  TB_API_BEGIN(ctx)
+  TB_REQUIRE(srs && cs && out && (fixed_values || cs->num_fixed == 0) && (sigma_values || cs->num_perm_columns == 0), "tb_circuit_load arguments");
+  TB_CUDA(cudaSetDevice(ctx->c.device));
+  *out = reinterpret_cast<tb_pk*>(circuit_load(&ctx->c, reinterpret_cast<const Srs*>(srs), cs, fixed_values, sigma_values));
+  TB_API_END(ctx)
+}
+void tb_pk_free(tb_pk* pk) { delete reinterpret_cast<Circuit*>(pk); }
+size_t tb_pk_proof_len(const tb_pk* pk) { return pk ? reinterpret_cast<const Circuit*>(pk)->proof_len : 0; }
+
+tb_status tb_prove_batch(tb_ctx* ctx, const tb_pk* pk, uint32_t n_proofs, const uint8_t* advice, const uint8_t* instance, const uint32_t* instance_len,
+                         const uint8_t seed[32], uint32_t first_proof_index, uint8_t* proofs_out, size_t proof_stride) {
+  TB_API_BEGIN(ctx)
+  const Circuit* C = reinterpret_cast<const Circuit*>(pk);
+  TB_REQUIRE(C && n_proofs >= 1 && advice && seed && proofs_out && proof_stride >= C->proof_len && (C->ni == 0 || (instance && instance_len)), "tb_prove_batch arguments");
+  TB_REQUIRE((uint64_t)n_proofs * std::max<uint32_t>(C->na, C->pieces) <= 65535, "batch too large for one call");
+  TB_CUDA(cudaSetDevice(ctx->c.device));
+  prove_batch(&ctx->c, *C, (int)n_proofs, advice, instance, instance_len, seed, first_proof_index, proofs_out, proof_stride);
+  TB_API_END(ctx)
+}
+
+}  // extern "C"

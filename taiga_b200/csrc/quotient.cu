@@ -1,0 +1,341 @@
+// Row-parallel evaluation of the PLONKish gate / lookup / permutation constraint polynomial (the quotient numerator)
+// and the grand-product helpers, for sm_100a.
+//
+// Replaces the h(X) construction of halo2_proofs `plonk::create_proof` + `vanishing::Argument::construct`,
+// `permutation::Argument::commit` and `lookup::Argument::commit_product` (EXT; SURVEY.md §8a rows H3-H5, App. A.1
+// step 8, App. E.3/E.6).  The extended domain is never materialised per column: for each of the R = 2^(ext_k-k)
+// sub-cosets zeta*w_ext^k1*<w> the per-proof columns are NTT'd onto that sub-coset (n rows), every constraint is
+// evaluated one thread per row, and the result is scaled by the (constant on the sub-coset) 1/(X^n - 1).
+//
+// Algorithmic bytes per sub-coset row: 32*(C+1), C = distinct column-cosets read.
+#include <map>
+#include "common.cuh"
+#include "prover_kernels.cuh"
+
+namespace tb {
+
+// ---------------------------------------------------------------- expression compiler (host)
+namespace {
+struct Compiler {
+  const tb_cs_desc* cs;
+  std::vector<int> refc;          // remaining uses per node
+  std::vector<int> reg_of;        // register holding node value (-1 = none)
+  std::vector<int> free_regs; int next_reg = 0, max_regs = 0;
+  std::vector<QInstr> code;
+  struct Opnd { int kind; uint32_t v; int node; };
+
+  explicit Compiler(const tb_cs_desc* c) : cs(c), refc(c->num_nodes, 0), reg_of(c->num_nodes, -1) {}
+  void count(uint32_t node, std::vector<char>& seen) {
+    refc[node]++;
+    if (seen[node]) return;
+    seen[node] = 1;
+    const tb_expr_node& nd = cs->nodes[node];
+    if (nd.op == TB_EX_NEG || nd.op == TB_EX_SCALE) count(nd.a, seen);
+    else if (nd.op == TB_EX_ADD || nd.op == TB_EX_MUL) { count(nd.a, seen); count(nd.b, seen); }
+  }
+  int alloc() {
+    int r;
+    if (!free_regs.empty()) { r = free_regs.back(); free_regs.pop_back(); } else r = next_reg++;
+    if (next_reg > max_regs) max_regs = next_reg;
+    return r;
+  }
+  void release(const Opnd& o) {
+    if (o.node < 0) return;
+    if (--refc[o.node] == 0 && reg_of[o.node] >= 0) { free_regs.push_back(reg_of[o.node]); reg_of[o.node] = -1; }
+  }
+  Opnd emit(uint32_t node) {
+    const tb_expr_node& nd = cs->nodes[node];
+    switch (nd.op) {
+      case TB_EX_CONST: return {K_CONST, nd.a, (int)node};
+      case TB_EX_ADVICE: return {K_ADV, nd.a, (int)node};
+      case TB_EX_FIXED: return {K_FIX, nd.a, (int)node};
+      case TB_EX_INSTANCE: return {K_INST, nd.a, (int)node};
+      default: break;
+    }
+    if (reg_of[node] >= 0) return {K_REG, (uint32_t)reg_of[node], (int)node};
+    int op; Opnd oa, ob; bool binary = true;
+    if (nd.op == TB_EX_NEG) { oa = emit(nd.a); ob = {K_CONST, 0, -1}; op = Q_NEG; binary = false; }
+    else if (nd.op == TB_EX_SCALE) { oa = emit(nd.a); ob = {K_CONST, nd.b, -1}; op = Q_MUL; }
+    else if (nd.op == TB_EX_MUL) { oa = emit(nd.a); ob = emit(nd.b); op = Q_MUL; }
+    else {  // ADD, with a - b peephole when the negation is used only here
+      const tb_expr_node& na = cs->nodes[nd.a]; const tb_expr_node& nb = cs->nodes[nd.b];
+      if (nb.op == TB_EX_NEG && refc[nd.b] == 1 && reg_of[nd.b] < 0) {
+        oa = emit(nd.a); refc[nd.b]--; ob = emit(nb.a); op = Q_SUB;
+      } else if (na.op == TB_EX_NEG && refc[nd.a] == 1 && reg_of[nd.a] < 0) {
+        oa = emit(nd.b); refc[nd.a]--; ob = emit(na.a); op = Q_SUB;
+      } else { oa = emit(nd.a); ob = emit(nd.b); op = Q_ADD; }
+    }
+    // operands of leaves carry node ids only for refcounting; leaves hold no register
+    release(oa); if (binary) release(ob);
+    int r = alloc();
+    code.push_back(q_make(op, r, oa.kind, oa.v, ob.kind, ob.v));
+    reg_of[node] = r;
+    return {K_REG, (uint32_t)r, (int)node};
+  }
+};
+void finish_program(Compiler& c, QProgram* out) {
+  out->host = c.code; out->nregs = c.max_regs < 1 ? 1 : c.max_regs; out->ninstr = (int)c.code.size();
+  TB_REQUIRE(out->nregs <= 96, "constraint expressions need too many live temporaries");
+  if (out->dev) cudaFree(out->dev);
+  out->dev = nullptr;
+  if (out->ninstr) {
+    TB_CUDA(cudaMalloc(&out->dev, out->ninstr * sizeof(QInstr)));
+    TB_CUDA(cudaMemcpy(out->dev, out->host.data(), out->ninstr * sizeof(QInstr), cudaMemcpyHostToDevice));
+  }
+}
+}  // namespace
+
+void q_compile_gates(const tb_cs_desc* cs, QProgram* out) {
+  Compiler c(cs);
+  std::vector<char> seen(cs->num_nodes, 0);
+  for (uint32_t i = 0; i < cs->num_constraints; ++i) c.count(cs->constraint_roots[i], seen);
+  for (uint32_t i = 0; i < cs->num_constraints; ++i) {
+    Compiler::Opnd o = c.emit(cs->constraint_roots[i]);
+    c.code.push_back(q_make(Q_FOLD_Y, 0, o.kind, o.v, K_CONST, 0));
+    c.release(o);
+  }
+  finish_program(c, out);
+}
+
+void q_compile_lookups(const tb_cs_desc* cs, QProgram* out) {
+  Compiler c(cs);
+  std::vector<char> seen(cs->num_nodes, 0);
+  for (uint32_t l = 0; l < cs->num_lookups; ++l)
+    for (uint32_t e = 0; e < cs->lookups[l].num_exprs; ++e) { c.count(cs->lookups[l].input_roots[e], seen); c.count(cs->lookups[l].table_roots[e], seen); }
+  for (uint32_t l = 0; l < cs->num_lookups; ++l) {
+    c.code.push_back(q_make(Q_LK_BEGIN, 0, K_CONST, 0, K_CONST, 0));
+    for (uint32_t e = 0; e < cs->lookups[l].num_exprs; ++e) {
+      Compiler::Opnd o = c.emit(cs->lookups[l].input_roots[e]);
+      c.code.push_back(q_make(Q_FOLD_A, 0, o.kind, o.v, K_CONST, 0)); c.release(o);
+    }
+    for (uint32_t e = 0; e < cs->lookups[l].num_exprs; ++e) {
+      Compiler::Opnd o = c.emit(cs->lookups[l].table_roots[e]);
+      c.code.push_back(q_make(Q_FOLD_S, 0, o.kind, o.v, K_CONST, 0)); c.release(o);
+    }
+    c.code.push_back(q_make(Q_LK_STORE, 0, K_CONST, l, K_CONST, 0));
+  }
+  finish_program(c, out);
+}
+
+// ---------------------------------------------------------------- interpreter kernel
+__global__ void q_interp_kernel(const QInstr* __restrict__ prog, int ninstr, int nregs, QData d) {
+  extern __shared__ uint4 q_smem[];
+  const int T = blockDim.x, tid = threadIdx.x;
+  uint4* rlo = q_smem;
+  uint4* rhi = q_smem + (size_t)nregs * T;
+  const int row = blockIdx.x * T + tid, b = blockIdx.y;
+  if (row >= d.n) return;
+  const int nm = d.n - 1;
+  const Fp* adv = d.adv + (long long)b * d.adv_pstride;
+  const Fp* inst = d.inst + (long long)b * d.inst_pstride;
+  const Fp y = d.chal[(long long)b * d.chal_stride + d.y_slot];
+  const Fp theta = d.chal[(long long)b * d.chal_stride + d.theta_slot];
+  Fp acc = Fp::zero(), accA = Fp::zero(), accS = Fp::zero();
+
+  auto fetch = [&](int kind, uint32_t v) -> Fp {
+    switch (kind) {
+      case K_REG: { uint4 x = rlo[v * T + tid], z = rhi[v * T + tid]; Fp r;
+        r.l[0] = x.x; r.l[1] = x.y; r.l[2] = x.z; r.l[3] = x.w; r.l[4] = z.x; r.l[5] = z.y; r.l[6] = z.z; r.l[7] = z.w; return r; }
+      case K_ADV: { int2 q = d.aq[v]; return ldg_fe(adv + (size_t)q.x * d.n + ((row + q.y + d.n) & nm)); }
+      case K_FIX: { int2 q = d.fq[v]; return ldg_fe(d.fix + ((size_t)q.x * d.R + d.k1) * d.n + ((row + q.y + d.n) & nm)); }
+      case K_INST: { int2 q = d.iq[v]; return ldg_fe(inst + (size_t)q.x * d.n + ((row + q.y + d.n) & nm)); }
+      default: return ldg_fe(d.consts + v);
+    }
+  };
+  for (int pc = 0; pc < ninstr; ++pc) {
+    const QInstr in = prog[pc];
+    const int op = in.w0 & 0xff, dst = (in.w0 >> 8) & 0xff, ak = (in.w0 >> 16) & 0xff, bk = in.w0 >> 24;
+    Fp r;
+    switch (op) {
+      case Q_MOV: r = fetch(ak, in.a); break;
+      case Q_NEG: r = fetch(ak, in.a).neg(); break;
+      case Q_ADD: r = fetch(ak, in.a) + fetch(bk, in.b); break;
+      case Q_SUB: r = fetch(ak, in.a) - fetch(bk, in.b); break;
+      case Q_MUL: r = fetch(ak, in.a) * fetch(bk, in.b); break;
+      case Q_FOLD_Y: acc = acc * y + fetch(ak, in.a); continue;
+      case Q_LK_BEGIN: accA = Fp::zero(); accS = Fp::zero(); continue;
+      case Q_FOLD_A: accA = accA * theta + fetch(ak, in.a); continue;
+      case Q_FOLD_S: accS = accS * theta + fetch(ak, in.a); continue;
+      case Q_LK_STORE: {
+        size_t o = (size_t)b * d.lk_pstride + (size_t)in.a * d.n + row;
+        st_fe(d.lkA + o, accA); st_fe(d.lkS + o, accS); continue; }
+      default: continue;
+    }
+    rlo[dst * T + tid] = make_uint4(r.l[0], r.l[1], r.l[2], r.l[3]);
+    rhi[dst * T + tid] = make_uint4(r.l[4], r.l[5], r.l[6], r.l[7]);
+  }
+  if (d.gate_out) st_fe(d.gate_out + (long long)b * d.gate_pstride + row, acc);
+}
+
+void q_run(Ctx* c, const QProgram& prog, const QData& d, int B) {
+  static bool attr = false;
+  if (!attr) { TB_CUDA(cudaFuncSetAttribute(q_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+  int T = (96 * 1024) / (prog.nregs * 32);
+  T = T >= 128 ? 128 : (T / 32) * 32;
+  TB_REQUIRE(T >= 32, "constraint program register file does not fit shared memory");
+  if (d.n < T) T = d.n < 32 ? 32 : d.n;
+  size_t smem = (size_t)prog.nregs * T * 32;
+  q_interp_kernel<<<dim3((d.n + T - 1) / T, B), T, smem, c->stream>>>(prog.dev, prog.ninstr, prog.nregs, d);
+  TB_LAUNCH_CHECK(); c->launches++;
+}
+
+// ---------------------------------------------------------------- permutation + lookup terms, vanishing division
+__global__ void __launch_bounds__(128) q_finish_kernel(QFinish f) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (row >= f.n) return;
+  const int n = f.n, nm = n - 1;
+  const Fp* chal = f.chal + (long long)b * f.chal_stride;
+  const Fp y = chal[f.y_slot], beta = chal[f.beta_slot], gamma = chal[f.gamma_slot];
+  const Fp one = Fp::one();
+  const size_t crow = (size_t)f.k1 * n + row;
+  Fp acc = ldg_fe(f.gate + (size_t)b * n + row);
+  const Fp l0 = ldg_fe(f.l0 + crow), ll = ldg_fe(f.l_last + crow);
+  const Fp active = one - (ll + ldg_fe(f.l_blind + crow));
+  const Fp* adv = f.adv + (long long)b * f.adv_pstride;
+  const Fp* inst = f.inst + (long long)b * f.inst_pstride;
+  if (f.nsets) {
+    const Fp* pz = f.pz + (long long)b * f.pz_pstride;
+    const int last_rot = -(f.bf + 1);
+    acc = acc * y + l0 * (one - ldg_fe(pz + row));
+    { Fp zl = ldg_fe(pz + (size_t)(f.nsets - 1) * n + row); acc = acc * y + ll * (zl * zl - zl); }
+    for (int s = 1; s < f.nsets; ++s)
+      acc = acc * y + l0 * (ldg_fe(pz + (size_t)s * n + row) - ldg_fe(pz + (size_t)(s - 1) * n + ((row + last_rot + n) & nm)));
+    // X on this sub-coset: zeta * w_ext^(k1 + R*row)
+    Fp xcur = f.zeta * tw_pow(f.tw, (uint32_t)(f.k1 + f.R * row) << (TW_LOG - f.ext_k));
+    for (int s = 0; s < f.nsets; ++s) {
+      int c0 = s * f.chunk, c1 = c0 + f.chunk < f.P ? c0 + f.chunk : f.P;
+      Fp left = ldg_fe(pz + (size_t)s * n + ((row + 1) & nm)), right = ldg_fe(pz + (size_t)s * n + row);
+      Fp cd = beta * f.delta_c0[s] * xcur;
+      for (int cidx = c0; cidx < c1; ++cidx) {
+        int2 col = f.perm_cols[cidx];
+        Fp val = col.x == TB_COL_ADVICE ? ldg_fe(adv + (size_t)col.y * n + row)
+               : col.x == TB_COL_FIXED ? ldg_fe(f.fix + ((size_t)col.y * f.R + f.k1) * n + row) : ldg_fe(inst + (size_t)col.y * n + row);
+        left = left * (val + beta * ldg_fe(f.sig + ((size_t)cidx * f.R + f.k1) * n + row) + gamma);
+        right = right * (val + cd + gamma);
+        cd = cd * f.delta;
+      }
+      acc = acc * y + (left - right) * active;
+    }
+  }
+  for (int l = 0; l < f.L; ++l) {
+    size_t o = (size_t)b * f.lk_pstride + (size_t)l * n;
+    Fp z = ldg_fe(f.lz + o + row), zn = ldg_fe(f.lz + o + ((row + 1) & nm));
+    Fp ap = ldg_fe(f.lpin + o + row), apm = ldg_fe(f.lpin + o + ((row - 1 + n) & nm)), sp = ldg_fe(f.lptab + o + row);
+    Fp a = ldg_fe(f.lkA + o + row), t = ldg_fe(f.lkS + o + row);
+    acc = acc * y + l0 * (one - z);
+    acc = acc * y + ll * (z * z - z);
+    acc = acc * y + (zn * (ap + beta) * (sp + gamma) - z * (a + beta) * (t + gamma)) * active;
+    acc = acc * y + l0 * (ap - sp);
+    acc = acc * y + (ap - sp) * (ap - apm) * active;
+  }
+  st_fe(f.out + (long long)b * f.out_pstride + crow, acc * f.t_inv);
+}
+
+void q_finish(Ctx* c, const QFinish& f, int B) {
+  q_finish_kernel<<<dim3((f.n + 127) / 128, B), 128, 0, c->stream>>>(f);
+  TB_LAUNCH_CHECK(); c->launches++;
+}
+
+// ---------------------------------------------------------------- extended_to_coeff, step B
+__global__ void h_cross_kernel(const Fp* __restrict__ V, long long v_pstride, Fp* __restrict__ hcoef, long long h_pstride, int n, int R, int pieces,
+                               const Fp* __restrict__ wr_inv, Fp r_inv, Fp zeta_inv) {
+  int i2 = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i2 >= n) return;
+  const Fp* v = V + (long long)b * v_pstride;
+  Fp zi2 = zeta_inv.sqr();
+  for (int i1 = 0; i1 < pieces; ++i1) {
+    Fp acc = Fp::zero();
+    for (int k1 = 0; k1 < R; ++k1) {
+      Fp x = ldg_fe(v + (size_t)k1 * n + i2);
+      int e = (i1 * k1) & (R - 1);
+      acc = acc + (e ? x * ldg_fe(wr_inv + e) : x);
+    }
+    acc = acc * r_inv;
+    uint32_t m3 = (uint32_t)((size_t)i1 * n + i2) % 3u;
+    if (m3) acc = acc * (m3 == 1 ? zeta_inv : zi2);
+    st_fe(hcoef + (long long)b * h_pstride + (size_t)i1 * n + i2, acc);
+  }
+}
+void h_cross(Ctx* c, const Fp* V, long long v_pstride, Fp* hcoef, long long h_pstride, int n, int R, int pieces, const Fp* d_wr_inv, Fp r_inv,
+             Fp zeta_inv, int B) {
+  h_cross_kernel<<<dim3((n + 127) / 128, B), 128, 0, c->stream>>>(V, v_pstride, hcoef, h_pstride, n, R, pieces, d_wr_inv, r_inv, zeta_inv);
+  TB_LAUNCH_CHECK(); c->launches++;
+}
+
+// ---------------------------------------------------------------- grand products
+__global__ void perm_fractions_kernel(PermFrac p) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y, b = blockIdx.z;
+  if (row >= p.n) return;
+  const int n = p.n;
+  const Fp* chal = p.chal + (long long)b * p.chal_stride;
+  const Fp beta = chal[p.beta_slot], gamma = chal[p.gamma_slot];
+  const Fp* adv = p.adv + (long long)b * p.adv_pstride;
+  const Fp* inst = p.inst + (long long)b * p.inst_pstride;
+  int c0 = s * p.chunk, c1 = c0 + p.chunk < p.P ? c0 + p.chunk : p.P;
+  Fp num = Fp::one(), den = Fp::one();
+  Fp dw = p.delta_c0[s] * tw_pow(p.tw, (uint32_t)row << (TW_LOG - p.k)) * beta;  // delta^c * omega^row * beta
+  for (int cidx = c0; cidx < c1; ++cidx) {
+    int2 col = p.perm_cols[cidx];
+    Fp val = col.x == TB_COL_ADVICE ? ldg_fe(adv + (size_t)col.y * n + row)
+           : col.x == TB_COL_FIXED ? ldg_fe(p.fix + (size_t)col.y * n + row) : ldg_fe(inst + (size_t)col.y * n + row);
+    den = den * (beta * ldg_fe(p.sig + (size_t)cidx * n + row) + gamma + val);
+    num = num * (dw + gamma + val);
+    dw = dw * p.delta;
+  }
+  size_t o = (size_t)b * p.pstride + (size_t)s * n + row;
+  st_fe(p.num + o, num); st_fe(p.den + o, den);
+}
+void perm_fractions(Ctx* c, const PermFrac& p, int B) {
+  if (!p.nsets) return;
+  perm_fractions_kernel<<<dim3((p.n + 127) / 128, p.nsets, B), 128, 0, c->stream>>>(p);
+  TB_LAUNCH_CHECK(); c->launches++;
+}
+
+__global__ void vec_mul_kernel(Fp* a, const Fp* b, size_t count) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) st_fe(a + i, ld_fe(a + i) * ld_fe(b + i));
+}
+void vec_mul(Ctx* c, Fp* a, const Fp* b, size_t count) {
+  if (!count) return;
+  vec_mul_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(a, b, count);
+  TB_LAUNCH_CHECK(); c->launches++;
+}
+
+__global__ void perm_carry_kernel(const Fp* z, long long pstride, int nsets, int n, int u, Fp* carries, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  Fp carry = Fp::one();
+  for (int s = 0; s < nsets; ++s) { carries[(size_t)b * nsets + s] = carry; carry = carry * z[(long long)b * pstride + (size_t)s * n + u]; }
+}
+__global__ void perm_scale_kernel(Fp* z, long long pstride, int nsets, int n, const Fp* carries) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y, b = blockIdx.z;
+  if (row >= n || s == 0) return;
+  Fp* p = z + (long long)b * pstride + (size_t)s * n + row;
+  st_fe(p, ld_fe(p) * carries[(size_t)b * nsets + s]);
+}
+void perm_chain(Ctx* c, Fp* z, long long pstride, int nsets, int n, int u, int B) {
+  if (nsets <= 1) return;
+  DevBuf<Fp> carries(c, (size_t)B * nsets);
+  perm_carry_kernel<<<(B + 31) / 32, 32, 0, c->stream>>>(z, pstride, nsets, n, u, carries.get(), B);
+  TB_LAUNCH_CHECK();
+  perm_scale_kernel<<<dim3((n + 255) / 256, nsets, B), 256, 0, c->stream>>>(z, pstride, nsets, n, carries.get());
+  TB_LAUNCH_CHECK(); c->launches += 2;
+}
+
+__global__ void lookup_fractions_kernel(const Fp* A, const Fp* S, const Fp* Ap, const Fp* Sp, Fp* num, Fp* den, long long pstride, int n,
+                                        const Fp* chal, long long chal_stride, int beta_slot, int gamma_slot) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x, l = blockIdx.y, b = blockIdx.z;
+  if (row >= n) return;
+  const Fp beta = chal[(long long)b * chal_stride + beta_slot], gamma = chal[(long long)b * chal_stride + gamma_slot];
+  size_t o = (size_t)b * pstride + (size_t)l * n + row;
+  st_fe(den + o, (beta + ld_fe(Ap + o)) * (gamma + ld_fe(Sp + o)));
+  st_fe(num + o, (ld_fe(A + o) + beta) * (ld_fe(S + o) + gamma));
+}
+void lookup_fractions(Ctx* c, const Fp* A, const Fp* S, const Fp* Ap, const Fp* Sp, Fp* num, Fp* den, long long pstride, int L, int n,
+                      const Fp* chal, long long chal_stride, int beta_slot, int gamma_slot, int B) {
+  if (!L) return;
+  lookup_fractions_kernel<<<dim3((n + 255) / 256, L, B), 256, 0, c->stream>>>(A, S, Ap, Sp, num, den, pstride, n, chal, chal_stride, beta_slot, gamma_slot);
+  TB_LAUNCH_CHECK(); c->launches++;
+}
+
+}  // namespace tb

@@ -46,6 +46,10 @@ _SIGS = {
     "tb_srs_load": (_i, [_vp, _u32, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
     "tb_srs_free": (None, [_vp]),
     "tb_srs_commit": (_i, [_vp, _vp, _i, _u32, _vp, _vp, _vp]),
+    "tb_circuit_load": (_i, [_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
+    "tb_pk_free": (None, [_vp]),
+    "tb_pk_proof_len": (_sz, [_vp]),
+    "tb_prove_batch": (_i, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _u32, _vp, _sz]),
 }
 
 
@@ -177,9 +181,55 @@ class Srs:
         self.ctx._check(self.ctx._lib.tb_srs_commit(self.ctx._h, self._h, int(lagrange), batch, _ptr(s), _ptr(b), _ptr(out)))
         return out
 
+    def load_circuit(self, keydata):
+        return ProvingKey(self, keydata)
+
     def close(self):
         if getattr(self, "_h", None):
             self.ctx._lib.tb_srs_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ProvingKey:
+    """Device-resident proving key of one circuit (tb_pk): the stand-in for halo2's ProvingKey<vesta::Affine>
+    (COMPLIANCE_PROVING_KEY / TRIVIAL_RESOURCE_LOGIC_PK, constant.rs:145-152, resource_logic_examples.rs:50-61).
+    `keydata` is a taiga_b200.circuit.CircuitKeyData (descriptor + fixed columns + sigma)."""
+
+    def __init__(self, srs, keydata):
+        self.srs, self.ctx, self.keydata = srs, srs.ctx, keydata
+        self._fixed, self._sigma = _u8(keydata.fixed), _u8(keydata.sigma)
+        h = _vp()
+        self.ctx._check(self.ctx._lib.tb_circuit_load(self.ctx._h, srs._h, ctypes.byref(keydata.desc), _ptr(self._fixed), _ptr(self._sigma), ctypes.byref(h)))
+        self._h = h
+        self.proof_len = int(self.ctx._lib.tb_pk_proof_len(h))
+
+    def prove_batch(self, advice, instance, instance_len, seed, first_proof_index=0):
+        """Proof::create for a batch: advice uint8 [B, num_advice, n, 32]; instance uint8 [B, sum(instance_len), 32].
+        Returns a list of B proof byte strings."""
+        adv = _u8(advice)
+        kd = self.keydata
+        per = kd.cs.num_advice * kd.n * 32
+        assert adv.size % per == 0
+        B = adv.size // per
+        inst = _u8(instance)
+        lens = np.ascontiguousarray(instance_len, dtype=np.uint32)
+        assert inst.size >= B * int(lens.sum()) * 32
+        seed = _u8(np.frombuffer(bytes(seed), np.uint8))
+        assert seed.size == 32
+        out = np.zeros((B, self.proof_len), np.uint8)
+        self.ctx._check(self.ctx._lib.tb_prove_batch(self.ctx._h, self._h, B, _ptr(adv), _ptr(inst), _ptr(lens), _ptr(seed), first_proof_index,
+                                                     _ptr(out), self.proof_len))
+        return [out[b].tobytes() for b in range(B)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.tb_pk_free(self._h)
             self._h = None
 
     def __del__(self):
