@@ -31,8 +31,14 @@ void poly_scale(Ctx* c, Fp* out, long long out_stride, const Fp* s, long long s_
   TB_LAUNCH_CHECK(); c->launches++;
 }
 
+__global__ void poly_copy_kernel(Fp* out, long long out_stride, const Fp* in, long long in_stride, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= n) return;
+  st_fe(out + (long long)b * out_stride + i, ld_fe(in + (long long)b * in_stride + i));
+}
 void poly_copy(Ctx* c, Fp* out, long long out_stride, const Fp* in, long long in_stride, int n, int B) {
-  TB_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(Fp), in, in_stride * sizeof(Fp), (size_t)n * sizeof(Fp), B, cudaMemcpyDeviceToDevice, c->stream));
+  poly_copy_kernel<<<dim3((n + PO_THREADS - 1) / PO_THREADS, B), PO_THREADS, 0, c->stream>>>(out, out_stride, in, in_stride, n);
+  TB_LAUNCH_CHECK(); c->launches++;
 }
 
 __global__ void poly_add_at_kernel(Fp* v, long long stride, int idx, const Fp* s, long long s_stride, int sign, int B) {

@@ -556,7 +556,7 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   { Prog p; p.op(S_MUL, V_F, V_S_BLIND, V_XI); p.op(S_ADD, V_F, V_F, V_P_BLIND); run_prog(p); }
   powers(ctx, bvec.get(), (long long)n, VP(V_X3), NV, (int)n, B);
   DevBuf<Aff<Fq>> gprime(ctx, (size_t)B * n);
-  TB_CUDA(cudaMemcpy2DAsync(gprime.get(), n * sizeof(Aff<Fq>), srs.g, 0, n * sizeof(Aff<Fq>), B, cudaMemcpyDeviceToDevice, st));
+  poly_copy(ctx, reinterpret_cast<Fp*>(gprime.get()), 2 * nn, reinterpret_cast<const Fp*>(srs.g), 0, (int)(2 * n), B);  // Aff<Fq> = 2 x 32 bytes
   DevBuf<Xyzz<Fq>> accL(ctx, B), accR(ctx, B);
   DevBuf<Aff<Fq>> ptL(ctx, B), ptR(ctx, B);
   DevBuf<Fp> ex(ctx, (size_t)B * 2);
