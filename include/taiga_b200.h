@@ -39,6 +39,12 @@ const char* tb_version(void);
 tb_status tb_ctx_sync(tb_ctx* ctx);
 uint64_t tb_ctx_stream(const tb_ctx* ctx);        /* cudaStream_t, for event timing by the caller */
 uint64_t tb_ctx_launch_count(const tb_ctx* ctx);  /* kernels launched through this context so far */
+/* Built-in CUDA-event profiler: when enabled every kernel group is bracketed by events on the context's stream;
+ * tb_prof_read synchronises and returns accumulated milliseconds and group counts per category, then resets. */
+int tb_prof_categories(void);
+const char* tb_prof_category_name(int category);
+tb_status tb_prof_enable(tb_ctx* ctx, int on);
+tb_status tb_prof_read(tb_ctx* ctx, double* ms_out, uint64_t* counts_out);
 
 /* ---- primitives over HOST buffers (copies in and out inside the call).
  * tb_ntt   replaces halo2_proofs arithmetic::best_fft / EvaluationDomain::{lagrange_to_coeff, coeff_to_lagrange}

@@ -53,6 +53,31 @@ tb_status tb_ctx_sync(tb_ctx* ctx) { TB_API_BEGIN(ctx) ctx->c.sync(); TB_API_END
 uint64_t tb_ctx_stream(const tb_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->c.stream : 0; }
 uint64_t tb_ctx_launch_count(const tb_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
 
+static const char* PROF_NAMES[PC_COUNT] = {"ntt", "msm_sort", "msm_accum", "msm_reduce", "quotient_gates", "quotient_finish", "ipa_fold", "transcript",
+                                           "lookup_sort", "poly"};
+int tb_prof_categories(void) { return PC_COUNT; }
+const char* tb_prof_category_name(int i) { return (i >= 0 && i < PC_COUNT) ? PROF_NAMES[i] : ""; }
+tb_status tb_prof_enable(tb_ctx* ctx, int on) {
+  TB_API_BEGIN(ctx)
+  ctx->c.sync();
+  for (auto& r : ctx->c.prof_recs) { ctx->c.event_pool.push_back(r.a); ctx->c.event_pool.push_back(r.b); }
+  ctx->c.prof_recs.clear();
+  ctx->c.prof = on != 0;
+  TB_API_END(ctx)
+}
+tb_status tb_prof_read(tb_ctx* ctx, double* ms_out, uint64_t* counts_out) {
+  TB_API_BEGIN(ctx)
+  ctx->c.sync();
+  for (int i = 0; i < PC_COUNT; ++i) { ms_out[i] = 0; counts_out[i] = 0; }
+  for (auto& r : ctx->c.prof_recs) {
+    float ms = 0; TB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_out[r.cat] += ms; counts_out[r.cat]++;
+    ctx->c.event_pool.push_back(r.a); ctx->c.event_pool.push_back(r.b);
+  }
+  ctx->c.prof_recs.clear();
+  TB_API_END(ctx)
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------- NTT

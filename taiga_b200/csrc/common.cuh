@@ -33,6 +33,11 @@ template <class F> struct FieldTables {
   TwiddleTables<F> fwd, inv;
 };
 
+// kernel categories for the built-in CUDA-event profiler (bench.py's roofline / share-of-step numbers)
+enum ProfCat { PC_NTT = 0, PC_MSM_SORT, PC_MSM_ACCUM, PC_MSM_REDUCE, PC_QUOT_GATES, PC_QUOT_FINISH, PC_IPA_FOLD, PC_TRANSCRIPT, PC_LOOKUP_SORT,
+               PC_POLY, PC_COUNT };
+struct ProfRec { int cat; cudaEvent_t a, b; };
+
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -41,6 +46,12 @@ struct Ctx {
   FieldTables<Fq> tw_fq;
   int sm_count = 148;
   uint64_t launches = 0;  // kernels launched through this context (bench's gpu_launches)
+  bool prof = false; std::vector<ProfRec> prof_recs; std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t get_event() {
+    cudaEvent_t e;
+    if (!event_pool.empty()) { e = event_pool.back(); event_pool.pop_back(); return e; }
+    TB_CUDA(cudaEventCreate(&e)); return e;
+  }
 
   template <class T> T* alloc(size_t count) {
     void* p = nullptr;
@@ -50,6 +61,18 @@ struct Ctx {
   }
   void free(void* p) { if (p) cudaFreeAsync(p, stream); }
   void sync() { TB_CUDA(cudaStreamSynchronize(stream)); }
+};
+
+// records a pair of CUDA events on the context's stream around a group of launches (only when profiling is on)
+struct ProfScope {
+  Ctx* c; int idx = -1;
+  ProfScope(Ctx* ctx, int cat) : c(ctx) {
+    if (!c->prof) return;
+    ProfRec r; r.cat = cat; r.a = c->get_event(); r.b = c->get_event();
+    cudaEventRecord(r.a, c->stream);
+    idx = (int)c->prof_recs.size(); c->prof_recs.push_back(r);
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(c->prof_recs[idx].b, c->stream); }
 };
 
 // RAII stream-ordered device buffer

@@ -64,6 +64,7 @@ __global__ void bitonic_global_kernel(Fp* keys, int n, int k, int j) {
 }
 
 void sort_keys(Ctx* c, Fp* keys, int n, int arrays) {
+  ProfScope prof_scope(c, PC_LOOKUP_SORT);
   TB_REQUIRE((n & (n - 1)) == 0, "sort needs a power-of-two length");
   static bool attr = false;
   if (!attr) { TB_CUDA(cudaFuncSetAttribute(bitonic_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_TILE * 32)); attr = true; }

@@ -11,6 +11,7 @@
 // warp-shuffle tree) -> Horner over windows.
 //
 // Algorithmic bytes: 96*N per MSM (64 B affine base + 32 B scalar); fixed-base batched: 64*N*W (tables) + 32*N*K.
+#include <memory>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -200,6 +201,7 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
   cudaStream_t st = ctx->stream;
 
   DevBuf<uint32_t> counts(ctx, nb_total), offs(ctx, nb_total + 1), cursor(ctx, nb_total), entries(ctx, max_entries);
+  std::unique_ptr<ProfScope> ps(new ProfScope(ctx, PC_MSM_SORT));
   counts.zero();
   dim3 dg((N + 255) / 256, K);
   msm_digits_kernel<S, 0><<<dg, 256, 0, st>>>(scalars, scalar_bstride, N, c, W, NB, wsep, table_mode, counts.get(), nullptr);
@@ -217,9 +219,11 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
   TB_LAUNCH_CHECK();
   exclusive_scan_u32(ctx, unit_count.get(), unit_off.get(), nb_total);
   DevBuf<Xyzz<B>> partial(ctx, max_units);
+  ps.reset(); ps.reset(new ProfScope(ctx, PC_MSM_ACCUM));
   msm_accum_kernel<B><<<(unsigned)((max_units + 127) / 128), 128, 0, st>>>(bases, base_bstride, (uint32_t)wsep * NB, offs.get(), unit_off.get(),
                                                                           nb_total, entries.get(), partial.get());
   TB_LAUNCH_CHECK();
+  ps.reset(); ps.reset(new ProfScope(ctx, PC_MSM_REDUCE));
   unsigned hgrid = (unsigned)(max_heavy < 1184 ? max_heavy : 1184);
   msm_heavy_kernel<B><<<hgrid, 256, 0, st>>>(heavy.get(), n_heavy.get(), unit_off.get(), partial.get());
   TB_LAUNCH_CHECK();

@@ -127,6 +127,7 @@ void ntt_run(Ctx* ctx, int logn, bool inverse, const F* in, F* out, F* scratch, 
              long long out_bstride, const NttHook<F>* pre, const NttHook<F>* post) {
   TB_REQUIRE(logn >= 1 && logn <= TW_LOG, "NTT size out of range");
   TB_REQUIRE(batch >= 1 && batch <= 65535, "NTT batch out of range");
+  ProfScope prof_scope(ctx, PC_NTT);
   static bool attr_set[2] = {false, false};
   if (!attr_set[F::params_id()]) {
     TB_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));

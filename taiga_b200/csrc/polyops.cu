@@ -17,6 +17,7 @@ __global__ void poly_fma_kernel(Fp* out, long long out_stride, const Fp* s, long
   st_fe(o, ld_fe(o) * sv + ld_fe(in + (long long)b * in_stride + i));
 }
 void poly_fma(Ctx* c, Fp* out, long long out_stride, const Fp* s, long long s_stride, const Fp* in, long long in_stride, int n, int B) {
+  ProfScope prof_scope(c, PC_POLY);
   poly_fma_kernel<<<dim3((n + PO_THREADS - 1) / PO_THREADS, B), PO_THREADS, 0, c->stream>>>(out, out_stride, s, s_stride, in, in_stride, n);
   TB_LAUNCH_CHECK(); c->launches++;
 }
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(PO_THREADS) poly_eval_kernel(const EvalItem* _
   if (threadIdx.x == 0) evals[(long long)b * ev_stride + t] = acc;
 }
 void poly_eval(Ctx* c, const EvalItem* d_items, int nitems, const Fp* points, long long pt_stride, Fp* evals, long long ev_stride, int n, int B) {
+  ProfScope prof_scope(c, PC_POLY);
   if (nitems <= 0) return;
   TB_REQUIRE((n & (n - 1)) == 0, "poly_eval needs a power-of-two length");
   poly_eval_kernel<<<dim3(nitems, B), PO_THREADS, 0, c->stream>>>(d_items, points, pt_stride, evals, ev_stride, n);
@@ -177,6 +179,7 @@ __global__ void __launch_bounds__(KD_THREADS) kate_div_kernel(Fp* out, long long
   }
 }
 void poly_kate_div(Ctx* c, Fp* out, long long out_stride, const Fp* in, long long in_stride, const Fp* z, long long z_stride, int n, int B) {
+  ProfScope prof_scope(c, PC_POLY);
   TB_REQUIRE((n & (n - 1)) == 0, "kate division needs a power-of-two length");
   static bool attr = false;
   if (!attr) { TB_CUDA(cudaFuncSetAttribute(kate_div_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * KD_THREADS * 32)); attr = true; }

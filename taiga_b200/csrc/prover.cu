@@ -302,7 +302,7 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   }
   // ---- advice columns: upload, blinding rows, commit, iNTT
   DevBuf<Fp> adv_vals(ctx, (size_t)B * na * n), adv_polys(ctx, (size_t)B * na * n);
-  TB_CUDA(cudaMemcpyAsync(adv_vals.get(), advice_host, (size_t)B * na * n * 32, cudaMemcpyHostToDevice, st));
+  TB_CUDA(cudaMemcpyAsync(adv_vals.get(), advice_host, (size_t)B * na * n * 32, cudaMemcpyDefault, st));  // host or device pointer
   fe_to_mont<Fp>(ctx, adv_vals.get(), (size_t)B * na * n);
   for (int c = 0; c < na; ++c)
     prf_fill(ctx, seed, proof0, R_ADVICE_ROWS, (uint32_t)(c * (bf + 1)), adv_vals.get() + (size_t)c * n + C.usable, (long long)na * n, 1, bf + 1, B);
@@ -584,6 +584,7 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
     tr.points(ptR.get(), 1, 1, true);
     tr.squeeze(VP(V_U), NV, 1);
     { Prog p; p.op(S_INV, V_UINV, V_U); p.op(S_MUL, V_T0, V_LR, V_UINV); p.op(S_ADD, V_F, V_F, V_T0); p.op(S_MUL, V_T0, V_RR, V_U); p.op(S_ADD, V_F, V_F, V_T0); run_prog(p); }
+    ProfScope fold_scope(ctx, PC_IPA_FOLD);
     ipa_fold_g_kernel<<<dim3((half + 63) / 64, B), 64, 0, st>>>(gprime.get(), (long long)n, half, vars.get(), NV, V_U);
     TB_LAUNCH_CHECK();
     ipa_fold_scalars_kernel<<<dim3((half + 127) / 128, B), 128, 0, st>>>(pprime.get(), bvec.get(), (long long)n, half, vars.get(), NV, V_U, V_UINV);

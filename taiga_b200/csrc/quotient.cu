@@ -168,6 +168,7 @@ __global__ void q_interp_kernel(const QInstr* __restrict__ prog, int ninstr, int
 }
 
 void q_run(Ctx* c, const QProgram& prog, const QData& d, int B) {
+  ProfScope prof_scope(c, PC_QUOT_GATES);
   static bool attr = false;
   if (!attr) { TB_CUDA(cudaFuncSetAttribute(q_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
   int T = (96 * 1024) / (prog.nregs * 32);
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(128) q_finish_kernel(QFinish f) {
 }
 
 void q_finish(Ctx* c, const QFinish& f, int B) {
+  ProfScope prof_scope(c, PC_QUOT_FINISH);
   q_finish_kernel<<<dim3((f.n + 127) / 128, B), 128, 0, c->stream>>>(f);
   TB_LAUNCH_CHECK(); c->launches++;
 }

@@ -148,14 +148,17 @@ void Transcripts::init(Ctx* c, int B_, uint32_t cap_, const Fp& vk_repr_canonica
   TB_LAUNCH_CHECK(); c->launches++;
 }
 void Transcripts::points(const Aff<Fq>* pts, long long stride, int count, bool write) {
+  ProfScope prof_scope(ctx, PC_TRANSCRIPT);
   tr_points_kernel<<<(B + 31) / 32, 32, 0, ctx->stream>>>(states.get(), proofs.get(), cap, B, pts, stride, count, write ? 1 : 0);
   TB_LAUNCH_CHECK(); ctx->launches++;
 }
 void Transcripts::scalars(const Fp* sc, long long stride, int count, bool write) {
+  ProfScope prof_scope(ctx, PC_TRANSCRIPT);
   tr_scalars_kernel<<<(B + 31) / 32, 32, 0, ctx->stream>>>(states.get(), proofs.get(), cap, B, sc, stride, count, write ? 1 : 0);
   TB_LAUNCH_CHECK(); ctx->launches++;
 }
 void Transcripts::squeeze(Fp* out, long long stride, int count) {
+  ProfScope prof_scope(ctx, PC_TRANSCRIPT);
   tr_squeeze_kernel<<<(B + 31) / 32, 32, 0, ctx->stream>>>(states.get(), B, out, stride, count);
   TB_LAUNCH_CHECK(); ctx->launches++;
 }

@@ -37,6 +37,10 @@ _SIGS = {
     "tb_ctx_sync": (_i, [_vp]),
     "tb_ctx_stream": (_u64, [_vp]),
     "tb_ctx_launch_count": (_u64, [_vp]),
+    "tb_prof_categories": (_i, []),
+    "tb_prof_category_name": (ctypes.c_char_p, [_i]),
+    "tb_prof_enable": (_i, [_vp, _i]),
+    "tb_prof_read": (_i, [_vp, _vp, _vp]),
     "tb_ntt": (_i, [_vp, _i, _u32, _i, _i, _u32, _vp, _vp]),
     "tb_msm": (_i, [_vp, _i, _sz, _u32, _vp, _vp, _u32, _vp]),
     "tb_dev_to_mont": (_i, [_vp, _i, _vp, _sz]),
@@ -125,6 +129,17 @@ class Context:
 
     def sync(self):
         self._check(self._lib.tb_ctx_sync(self._h))
+
+    def prof_enable(self, on=True):
+        self._check(self._lib.tb_prof_enable(self._h, int(on)))
+
+    def prof_read(self):
+        """{category: (milliseconds, kernel groups)} since the last read, measured with CUDA events on the context's stream."""
+        n = self._lib.tb_prof_categories()
+        ms = np.zeros(n, np.float64)
+        cnt = np.zeros(n, np.uint64)
+        self._check(self._lib.tb_prof_read(self._h, _ptr(ms), _ptr(cnt)))
+        return {self._lib.tb_prof_category_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
 
     # ---- host-buffer primitives
     def ntt(self, field, data, inverse=False, coset=False, batch=1):
