@@ -20,7 +20,10 @@ template <class F> void free_twiddles(Ctx* ctx);
 // ---------------------------------------------------------------- MSM (msm.cu)
 struct MsmConfig {
   int c = 0;             // window bits (0 = choose from N)
-  int table_windows = 0;  // >0: `bases` is a fixed-base table [table_windows][N] of 2^(c*w)*B_i and all windows share one bucket set
+  int table_windows = 0;  // >0: `bases` is a fixed-base table [table_windows][table_stride] of 2^(c*w)*B_i and all windows share one bucket set
+  int table_stride = 0;   // points per table window (>= N + n_extra); 0 = N
+  int n_extra = 0;        // extra terms per MSM: scalar extra_scalars[k*n_extra + j] (Montgomery) times table point N + j
+  const void* extra_scalars = nullptr;
 };
 int msm_default_window(int n, bool fixed_tables);
 // K multi-scalar multiplications of N terms.  scalars: Montgomery form, item k at scalars + k*scalar_bstride.
@@ -30,6 +33,7 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
              const MsmConfig& cfg, Xyzz<B>* out);
 // table[w][i] = 2^(c*w) * bases[i], w < windows  (one-off, at SRS load)
 template <class B> void msm_build_tables(Ctx* ctx, const Aff<B>* bases, int N, int c, int windows, Aff<B>* table);
+template <class B> void points_to_affine(Ctx* ctx, const Xyzz<B>* acc, int K, Aff<B>* out);
 // out[k] = affine(acc[k] + sum_j extra_scalars[k*n_extra+j] * extra_bases[j]); scalars Montgomery
 template <class B, class S>
 void points_finalize(Ctx* ctx, const Xyzz<B>* acc, int K, const S* extra_scalars, const Aff<B>* extra_bases, int n_extra, Aff<B>* out);

@@ -39,11 +39,13 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int bit, int 
 // MODE 0: histogram, MODE 1: scatter
 template <class S, int MODE>
 __global__ void msm_digits_kernel(const S* __restrict__ scalars, long long sstride, int N, int c, int W, int NB, int wsep,
-                                  int table_mode, uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries) {
+                                  int table_mode, int table_stride, const S* __restrict__ extras, int n_extra,
+                                  uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int k = blockIdx.y;
-  if (i >= N) return;
-  S s = ldg_fe(scalars + (long long)k * sstride + i).from_mont();
+  if (i >= N + n_extra) return;
+  // terms N .. N+n_extra-1 are the extra (scalar, base) pairs appended to the fixed-base table (blind * w, value * u)
+  S s = (i < N ? ldg_fe(scalars + (long long)k * sstride + i) : ldg_fe(extras + (long long)k * n_extra + (i - N))).from_mont();
   if (s.is_zero()) return;
   const uint32_t half = 1u << (c - 1);
   uint32_t carry = 0;
@@ -56,7 +58,7 @@ __global__ void msm_digits_kernel(const S* __restrict__ scalars, long long sstri
       if (MODE == 0) atomicAdd(&counts_or_cursor[b], 1u);
       else {
         uint32_t pos = atomicAdd(&counts_or_cursor[b], 1u);
-        entries[pos] = (table_mode ? (uint32_t)(w * N + i) : (uint32_t)i) | (neg << 31);
+        entries[pos] = (table_mode ? (uint32_t)(w * table_stride + i) : (uint32_t)i) | (neg << 31);
       }
     }
   }
@@ -195,20 +197,23 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
   const int NB = 1 << (c - 1);
   const int wsep = table_mode ? 1 : W;
   const uint64_t nb_total64 = (uint64_t)K * wsep * NB;
-  const uint64_t max_entries = (uint64_t)K * N * W;
-  TB_REQUIRE(nb_total64 < (1ull << 31) && max_entries < (1ull << 32) && (uint64_t)N * (table_mode ? W : 1) < (1ull << 31), "MSM too large");
+  const int n_extra = table_mode ? cfg_in.n_extra : 0;
+  const int table_stride = table_mode ? (cfg_in.table_stride ? cfg_in.table_stride : N) : 0;
+  const uint64_t max_entries = (uint64_t)K * (N + n_extra) * W;
+  TB_REQUIRE(nb_total64 < (1ull << 31) && max_entries < (1ull << 32) && (uint64_t)(N + 2) * (table_mode ? W : 1) < (1ull << 31), "MSM too large");
   const uint32_t nb_total = (uint32_t)nb_total64;
   cudaStream_t st = ctx->stream;
 
   DevBuf<uint32_t> counts(ctx, nb_total), offs(ctx, nb_total + 1), cursor(ctx, nb_total), entries(ctx, max_entries);
   std::unique_ptr<ProfScope> ps(new ProfScope(ctx, PC_MSM_SORT));
   counts.zero();
-  dim3 dg((N + 255) / 256, K);
-  msm_digits_kernel<S, 0><<<dg, 256, 0, st>>>(scalars, scalar_bstride, N, c, W, NB, wsep, table_mode, counts.get(), nullptr);
+  dim3 dg((N + n_extra + 255) / 256, K);
+  const S* extras = reinterpret_cast<const S*>(cfg_in.extra_scalars);
+  msm_digits_kernel<S, 0><<<dg, 256, 0, st>>>(scalars, scalar_bstride, N, c, W, NB, wsep, table_mode, table_stride, extras, n_extra, counts.get(), nullptr);
   TB_LAUNCH_CHECK();
   exclusive_scan_u32(ctx, counts.get(), offs.get(), nb_total);
   TB_CUDA(cudaMemcpyAsync(cursor.get(), offs.get(), nb_total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-  msm_digits_kernel<S, 1><<<dg, 256, 0, st>>>(scalars, scalar_bstride, N, c, W, NB, wsep, table_mode, cursor.get(), entries.get());
+  msm_digits_kernel<S, 1><<<dg, 256, 0, st>>>(scalars, scalar_bstride, N, c, W, NB, wsep, table_mode, table_stride, extras, n_extra, cursor.get(), entries.get());
   TB_LAUNCH_CHECK();
 
   const uint64_t max_heavy = max_entries / MSM_CHUNK + 1;
@@ -270,6 +275,18 @@ void msm_build_tables(Ctx* ctx, const Aff<B>* bases, int N, int c, int windows, 
 }
 template void msm_build_tables<Fq>(Ctx*, const Aff<Fq>*, int, int, int, Aff<Fq>*);
 template void msm_build_tables<Fp>(Ctx*, const Aff<Fp>*, int, int, int, Aff<Fp>*);
+
+template <class B>
+__global__ void points_to_affine_kernel(const Xyzz<B>* __restrict__ acc, int K, Aff<B>* __restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < K) out[k] = acc[k].to_affine();
+}
+template <class B> void points_to_affine(Ctx* ctx, const Xyzz<B>* acc, int K, Aff<B>* out) {
+  points_to_affine_kernel<B><<<(K + 31) / 32, 32, 0, ctx->stream>>>(acc, K, out);
+  TB_LAUNCH_CHECK(); ctx->launches++;
+}
+template void points_to_affine<Fq>(Ctx*, const Xyzz<Fq>*, int, Aff<Fq>*);
+template void points_to_affine<Fp>(Ctx*, const Xyzz<Fp>*, int, Aff<Fp>*);
 
 // ---------------------------------------------------------------- finalisation: + sum extra_scalar * extra_base, to affine
 template <class B, class S>

@@ -19,6 +19,7 @@ namespace tb {
 enum PolyKind { PK_INST = 0, PK_ADV, PK_PZ, PK_LZ, PK_LPIN, PK_LPTAB, PK_FIXED, PK_SIG, PK_H, PK_RANDOM };
 struct PolyId { int kind, idx; bool operator<(const PolyId& o) const { return kind != o.kind ? kind < o.kind : idx < o.idx; } bool operator==(const PolyId& o) const { return kind == o.kind && idx == o.idx; } };
 struct QueryRef { PolyId poly; int rot; };
+struct WsBlock { void* p = nullptr; size_t bytes = 0; };
 
 struct Circuit {
   Ctx* ctx; const Srs* srs;
@@ -41,8 +42,13 @@ struct Circuit {
   std::vector<int> rots;                  // distinct rotations (evaluation points), in order of first appearance in `queries`
   std::vector<PolyId> uniq; std::vector<int> uniq_set; std::vector<std::vector<int>> point_sets;
   uint32_t proof_len;
+  // persistent per-batch-size workspace and cached small tables (see prove_batch)
+  mutable std::map<int, std::vector<WsBlock>> ws;
+  mutable std::map<int, std::vector<void*>> cached_tables;
 
   ~Circuit() {
+    for (auto& kv : ws) for (auto& b : kv.second) cudaFree(b.p);
+    for (auto& kv : cached_tables) for (void* p : kv.second) cudaFree(p);
     for (void* p : {(void*)fixed_vals, (void*)fixed_polys, (void*)fixed_cosets, (void*)sig_vals, (void*)sig_polys, (void*)sig_cosets, (void*)l0, (void*)l_last,
                     (void*)l_blind, (void*)consts, (void*)wr_inv, (void*)d_aq, (void*)d_fq, (void*)d_iq, (void*)d_perm, (void*)prog_gates.dev, (void*)prog_lookups.dev})
       if (p) cudaFree(p);
@@ -200,34 +206,44 @@ static Circuit* circuit_load(Ctx* ctx, const Srs* srs, const tb_cs_desc* cs, con
   return Cp.release();
 }
 
-// ---------------------------------------------------------------- IPA folding kernels
-__global__ void ipa_fold_g_kernel(Aff<Fq>* g, long long stride, int half, const Fp* vars, long long vstride, int u_slot) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-  if (i >= half) return;
-  Aff<Fq>* gb = g + (long long)b * stride;
-  Fp u = vars[(long long)b * vstride + u_slot].from_mont();
-  Xyzz<Fq> acc = scalar_mul(gb[i + half], u.l);
-  acc.add_affine(gb[i]);
-  gb[i] = acc.to_affine();
+// ---------------------------------------------------------------- IPA kernels (s-vector form)
+// After j rounds the folded generators are G'_i = sum_q s_j(q) g[i + m q] (m = n >> j), so L_j / R_j are fixed-base MSMs over
+// the ORIGINAL generators with scalars p'[.] * s(t): no generator folding, no variable-base MSM, no Horner over windows.
+//   cL[t] = p'[half + i] * s[t]  if i <  half      cR[t] = p'[i - half] * s[t]  if i >= half      (i = t mod m, half = m/2)
+__global__ void ipa_round_scalars_kernel(const Fp* __restrict__ pprime, const Fp* __restrict__ sfull, Fp* __restrict__ cLR, int n, int m) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (t >= n) return;
+  int i = t & (m - 1), half = m >> 1;
+  const Fp* pp = pprime + (size_t)b * n;
+  Fp s = ld_fe(sfull + (size_t)b * n + t);
+  Fp* out = cLR + (size_t)b * 2 * n;
+  if (i < half) { st_fe(out + t, ld_fe(pp + half + i) * s); st_fe(out + n + t, Fp::zero()); }
+  else { st_fe(out + t, Fp::zero()); st_fe(out + n + t, ld_fe(pp + i - half) * s); }
 }
-__global__ void ipa_fold_scalars_kernel(Fp* p, Fp* bv, long long stride, int half, const Fp* vars, long long vstride, int u_slot, int uinv_slot) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-  if (i >= half) return;
-  Fp u = vars[(long long)b * vstride + u_slot], ui = vars[(long long)b * vstride + uinv_slot];
-  Fp* pb = p + (long long)b * stride; Fp* bb = bv + (long long)b * stride;
-  st_fe(pb + i, ld_fe(pb + i) + ld_fe(pb + i + half) * ui);
-  st_fe(bb + i, ld_fe(bb + i) + ld_fe(bb + i + half) * u);
+// p'[i] += p'[i+half] / u ; b[i] += b[i+half] * u  (i < half);  s[t] *= u for t with bit log2(half) set
+__global__ void ipa_fold_kernel(Fp* p, Fp* bv, Fp* sfull, int n, int half, const Fp* vars, long long vstride, int u_slot, int uinv_slot) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (t >= n) return;
+  Fp u = vars[(long long)b * vstride + u_slot];
+  if (t & half) { Fp* sp = sfull + (size_t)b * n + t; st_fe(sp, ld_fe(sp) * u); }
+  if (t < half) {
+    Fp ui = vars[(long long)b * vstride + uinv_slot];
+    Fp* pb = p + (size_t)b * n; Fp* bb = bv + (size_t)b * n;
+    st_fe(pb + t, ld_fe(pb + t) + ld_fe(pb + t + half) * ui);
+    st_fe(bb + t, ld_fe(bb + t) + ld_fe(bb + t + half) * u);
+  }
 }
-__global__ void fill_rows_const_kernel(Fp* v, long long stride, int row0, int count, Fp val, int B) {
-  int id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= B * count) return;
-  v[(long long)(id / count) * stride + row0 + id % count] = val;
+// extras[b][0] = {lr, vl*z}, extras[b][1] = {rr, vr*z}   (multipliers of the SRS points w and u)
+__global__ void ipa_extras_kernel(Fp* ex, const Fp* vars, long long vstride, int lr, int rr, int vl, int vr, int z, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const Fp* v = vars + (long long)b * vstride;
+  Fp* e = ex + (size_t)b * 4;
+  e[0] = v[lr]; e[1] = v[vl] * v[z]; e[2] = v[rr]; e[3] = v[vr] * v[z];
 }
-__global__ void gather_vars_kernel(Fp* out, long long ostride, const Fp* vars, long long vstride, const int* slots, int count, int B) {
-  int id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= B * count) return;
-  int b = id / count, i = id % count;
-  out[(long long)b * ostride + i] = vars[(long long)b * vstride + slots[i]];
+__global__ void fill_const_kernel(Fp* v, size_t count, Fp val) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) st_fe(v + i, val);
 }
 
 // ---------------------------------------------------------------- the prover
@@ -239,15 +255,44 @@ struct Prog {
   std::vector<ScalarInstr> ins;
   void op(int o, int dst, int a = 0, int b = 0, uint32_t imm = 0) { ScalarInstr i; i.op = (uint16_t)o; i.dst = (uint16_t)dst; i.a = (uint16_t)a; i.b = (uint16_t)b; i.imm = imm; ins.push_back(i); }
 };
+// Persistent per-(circuit, batch size) device workspace: the same sequence of requests returns the same pointers on every
+// call, so item tables / scalar programs that embed them are uploaded once and no allocation or host sync happens later.
+template <class T> struct WBuf {
+  T* p = nullptr; size_t n = 0; Ctx* ctx = nullptr;
+  T* get() const { return p; }
+  void zero() { TB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx->stream)); }
+};
+struct WsAlloc {
+  Ctx* ctx; std::vector<WsBlock>& blocks; size_t cur = 0;
+  template <class T> WBuf<T> buf(size_t count) {
+    size_t bytes = std::max<size_t>(1, count) * sizeof(T);
+    if (cur == blocks.size()) { WsBlock b; b.bytes = bytes; TB_CUDA(cudaMalloc(&b.p, bytes)); blocks.push_back(b); }
+    else if (blocks[cur].bytes < bytes) { cudaFree(blocks[cur].p); blocks[cur].bytes = bytes; TB_CUDA(cudaMalloc(&blocks[cur].p, bytes)); }
+    WBuf<T> w; w.p = reinterpret_cast<T*>(blocks[cur].p); w.n = count; w.ctx = ctx; ++cur;
+    return w;
+  }
+};
 
 static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice_host, const uint8_t* instance_host, const uint32_t* instance_len,
                         const uint8_t* seed, uint32_t proof0, uint8_t* proofs_out, size_t proof_stride) {
   const Srs& srs = *C.srs;
-  const size_t n = C.n; const int k = (int)C.k; const int na = C.na, ni = C.ni, L = C.L, nsets = C.nsets, P = C.P, bf = C.bf;
+  const size_t n = C.n; const long long nn = (long long)n; const int k = (int)C.k; const int na = C.na, ni = C.ni, L = C.L, nsets = C.nsets, P = C.P, bf = C.bf;
   const int ni1 = std::max(1, ni), L1 = std::max(1, L), ns1 = std::max(1, nsets);
   cudaStream_t st = ctx->stream;
   size_t inst_total = 0;
   for (int c = 0; c < ni; ++c) { TB_REQUIRE(instance_len[c] <= C.usable, "InstanceTooLarge"); inst_total += instance_len[c]; }
+  WsAlloc ws{ctx, C.ws[B]};
+  std::vector<void*>& tables = C.cached_tables[B];
+  size_t table_cur = 0;
+  // uploads a small host table once per (circuit, B); later calls reuse the device copy (contents are identical)
+  auto cached_upload = [&](const void* host, size_t bytes) -> void* {
+    if (table_cur == tables.size()) {
+      void* d = nullptr; TB_CUDA(cudaMalloc(&d, std::max<size_t>(16, bytes)));
+      TB_CUDA(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+      tables.push_back(d);
+    }
+    return tables[table_cur++];
+  };
 
   // ---- per-proof scalar variables
   VarAlloc va;
@@ -258,32 +303,30 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   const int V_RANDOM_BLIND = va.one(), V_H_BLINDS = va.one(C.pieces), V_H_BLIND = va.one(), V_QPRIME_BLIND = va.one();
   const int nps = (int)C.point_sets.size();
   const int V_QBLIND = va.one(nps), V_P_BLIND = va.one(), V_S_BLIND = va.one(), V_F = va.one();
-  const int V_S_AT = va.one(), V_V = va.one(), V_LR = va.one(), V_RR = va.one(), V_VL = va.one(), V_VR = va.one(), V_VLZ = va.one(), V_VRZ = va.one();
+  const int V_S_AT = va.one(), V_V = va.one(), V_LR = va.one(), V_RR = va.one(), V_VL = va.one(), V_VR = va.one();
   const int V_U = va.one(), V_UINV = va.one(), V_T0 = va.one(), V_C = va.one();
   const int NV = va.next;
-  DevBuf<Fp> vars(ctx, (size_t)B * NV);
+  WBuf<Fp> vars = ws.buf<Fp>((size_t)B * NV);
   vars.zero();
   std::vector<Fp> hconsts = {Fp::one(), C.omega, C.omega.inv()};
-  DevBuf<Fp> dconsts(ctx, hconsts.size()); dconsts.upload(hconsts.data(), hconsts.size());
-  DevBuf<ScalarInstr> dprog(ctx, 4096);
+  Fp* dconsts = reinterpret_cast<Fp*>(cached_upload(hconsts.data(), hconsts.size() * sizeof(Fp)));
   auto run_prog = [&](Prog& p) {
     if (p.ins.empty()) return;
-    TB_REQUIRE(p.ins.size() <= 4096, "scalar program too long");
-    // stream-ordered upload from a host vector that dies at scope end: stage through a pinned-free synchronous copy
-    TB_CUDA(cudaMemcpyAsync(dprog.get(), p.ins.data(), p.ins.size() * sizeof(ScalarInstr), cudaMemcpyHostToDevice, st));
-    TB_CUDA(cudaStreamSynchronize(st));
-    scalar_program(ctx, vars.get(), NV, dprog.get(), (int)p.ins.size(), dconsts.get(), B);
+    ScalarInstr* d = reinterpret_cast<ScalarInstr*>(cached_upload(p.ins.data(), p.ins.size() * sizeof(ScalarInstr)));
+    scalar_program(ctx, vars.get(), NV, d, (int)p.ins.size(), dconsts, B);
     p.ins.clear();
   };
   { Prog p; p.op(S_CONST, V_ONE, 0, 0, 0); run_prog(p); }
   auto VP = [&](int slot) { return vars.get() + slot; };  // pointer to slot of proof 0, stride NV
 
   Transcripts tr; tr.init(ctx, B, C.proof_len, C.vk_repr);
-  DevBuf<Fp> scratch(ctx, (size_t)B * std::max({na, ni1, L1 * 3, ns1, (int)C.pieces, 4}) * n);
-  DevBuf<Aff<Fq>> pts(ctx, (size_t)B * std::max({na, ni1, 2 * L1, ns1, (int)C.pieces, 2}));
+  WBuf<Fp> scratch = ws.buf<Fp>((size_t)B * std::max({na, ni1, L1 * 3, ns1, (int)C.pieces, 4}) * n);
+  WBuf<Aff<Fq>> pts = ws.buf<Aff<Fq>>((size_t)B * std::max({na, ni1, 2 * L1, ns1, (int)C.pieces, 2}));
+  WBuf<Fp> blinds = ws.buf<Fp>((size_t)B * std::max({na, ni1, L1, ns1, (int)C.pieces, 4}));
+  WBuf<uint32_t> derr = ws.buf<uint32_t>(1); derr.zero();
 
   // ---- instance columns: pad, commit_lagrange(Blind::default() = 1) -> common_point, iNTT
-  DevBuf<Fp> inst_vals(ctx, (size_t)B * ni1 * n), inst_polys(ctx, (size_t)B * ni1 * n);
+  WBuf<Fp> inst_vals = ws.buf<Fp>((size_t)B * ni1 * n), inst_polys = ws.buf<Fp>((size_t)B * ni1 * n);
   inst_vals.zero();
   if (ni) {
     size_t off = 0;
@@ -294,164 +337,155 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
       off += instance_len[c];
     }
     fe_to_mont<Fp>(ctx, inst_vals.get(), (size_t)B * ni * n);
-    DevBuf<Fp> ones(ctx, (size_t)B * ni);
-    fill_rows_const_kernel<<<(B * ni + 63) / 64, 64, 0, st>>>(ones.get(), ni, 0, ni, Fp::one(), B);
-    srs.commit(ctx, true, inst_vals.get(), (long long)n, B * ni, ones.get(), pts.get());
+    fill_const_kernel<<<(B * ni + 63) / 64, 64, 0, st>>>(blinds.get(), (size_t)B * ni, Fp::one());
+    srs.commit(ctx, true, inst_vals.get(), nn, B * ni, blinds.get(), pts.get());
     tr.points(pts.get(), ni, ni, false);
-    ntt_run<Fp>(ctx, k, true, inst_vals.get(), inst_polys.get(), scratch.get(), B * ni, (long long)n, (long long)n, nullptr, nullptr);
+    ntt_run<Fp>(ctx, k, true, inst_vals.get(), inst_polys.get(), scratch.get(), B * ni, nn, nn, nullptr, nullptr);
   }
   // ---- advice columns: upload, blinding rows, commit, iNTT
-  DevBuf<Fp> adv_vals(ctx, (size_t)B * na * n), adv_polys(ctx, (size_t)B * na * n);
+  WBuf<Fp> adv_vals = ws.buf<Fp>((size_t)B * na * n), adv_polys = ws.buf<Fp>((size_t)B * na * n);
   TB_CUDA(cudaMemcpyAsync(adv_vals.get(), advice_host, (size_t)B * na * n * 32, cudaMemcpyDefault, st));  // host or device pointer
   fe_to_mont<Fp>(ctx, adv_vals.get(), (size_t)B * na * n);
   for (int c = 0; c < na; ++c)
-    prf_fill(ctx, seed, proof0, R_ADVICE_ROWS, (uint32_t)(c * (bf + 1)), adv_vals.get() + (size_t)c * n + C.usable, (long long)na * n, 1, bf + 1, B);
+    prf_fill(ctx, seed, proof0, R_ADVICE_ROWS, (uint32_t)(c * (bf + 1)), adv_vals.get() + (size_t)c * n + C.usable, (long long)na * nn, 1, bf + 1, B);
   prf_fill(ctx, seed, proof0, R_ADVICE_BLIND, 0, VP(V_ADV_BLIND), NV, 1, na, B);
-  { DevBuf<Fp> blinds(ctx, (size_t)B * na);
-    poly_copy(ctx, blinds.get(), na, VP(V_ADV_BLIND), NV, na, B);
-    srs.commit(ctx, true, adv_vals.get(), (long long)n, B * na, blinds.get(), pts.get()); }
+  poly_copy(ctx, blinds.get(), na, VP(V_ADV_BLIND), NV, na, B);
+  srs.commit(ctx, true, adv_vals.get(), nn, B * na, blinds.get(), pts.get());
   tr.points(pts.get(), na, na, true);
-  ntt_run<Fp>(ctx, k, true, adv_vals.get(), adv_polys.get(), scratch.get(), B * na, (long long)n, (long long)n, nullptr, nullptr);
+  ntt_run<Fp>(ctx, k, true, adv_vals.get(), adv_polys.get(), scratch.get(), B * na, nn, nn, nullptr, nullptr);
   tr.squeeze(VP(V_THETA), NV, 1);
 
   // ---- lookups: compress (Lagrange domain), sort, arrange, blind, commit A', S'
-  DevBuf<Fp> lkA(ctx, (size_t)B * L1 * n), lkS(ctx, (size_t)B * L1 * n), lpin(ctx, (size_t)B * L1 * n), lptab(ctx, (size_t)B * L1 * n);
-  DevBuf<Fp> lpin_polys(ctx, (size_t)B * L1 * n), lptab_polys(ctx, (size_t)B * L1 * n);
+  WBuf<Fp> lkA = ws.buf<Fp>((size_t)B * L1 * n), lkS = ws.buf<Fp>((size_t)B * L1 * n), lpin = ws.buf<Fp>((size_t)B * L1 * n), lptab = ws.buf<Fp>((size_t)B * L1 * n);
+  WBuf<Fp> lpin_polys = ws.buf<Fp>((size_t)B * L1 * n), lptab_polys = ws.buf<Fp>((size_t)B * L1 * n);
   QData qd; memset(&qd, 0, sizeof(qd));
   qd.aq = C.d_aq; qd.fq = C.d_fq; qd.iq = C.d_iq; qd.consts = C.consts; qd.chal = vars.get(); qd.chal_stride = NV; qd.y_slot = V_Y; qd.theta_slot = V_THETA;
-  qd.n = (int)n; qd.lk_pstride = (long long)L1 * n;
+  qd.n = (int)n; qd.lk_pstride = (long long)L1 * nn;
   if (L) {
-    qd.adv = adv_vals.get(); qd.adv_pstride = (long long)na * n; qd.inst = inst_vals.get(); qd.inst_pstride = (long long)ni1 * n;
+    qd.adv = adv_vals.get(); qd.adv_pstride = (long long)na * nn; qd.inst = inst_vals.get(); qd.inst_pstride = (long long)ni1 * nn;
     qd.fix = C.fixed_vals; qd.R = 1; qd.k1 = 0; qd.gate_out = nullptr; qd.lkA = lkA.get(); qd.lkS = lkS.get();
     q_run(ctx, C.prog_lookups, qd, B);
-    DevBuf<Fp> keysA(ctx, (size_t)B * L * n), keysS(ctx, (size_t)B * L * n), left(ctx, (size_t)B * L * n);
-    DevBuf<uint32_t> derr(ctx, 1); derr.zero();
+    WBuf<Fp> keysA = ws.buf<Fp>((size_t)B * L * n), keysS = ws.buf<Fp>((size_t)B * L * n), left = ws.buf<Fp>((size_t)B * L * n);
     lookup_keys(ctx, keysA.get(), lkA.get(), (int)n, (int)C.usable, B * L);
     lookup_keys(ctx, keysS.get(), lkS.get(), (int)n, (int)C.usable, B * L);
     sort_keys(ctx, keysA.get(), (int)n, B * L);
     sort_keys(ctx, keysS.get(), (int)n, B * L);
-    lookup_arrange(ctx, keysA.get(), keysS.get(), left.get(), lptab.get(), (int)n, (int)C.usable, B * L, derr.get());
-    uint32_t herr = 0; TB_CUDA(cudaMemcpyAsync(&herr, derr.get(), 4, cudaMemcpyDeviceToHost, st)); ctx->sync();
-    if (herr) throw ConstraintError("lookup input not contained in the table (ConstraintSystemFailure)");
+    lookup_arrange(ctx, keysA.get(), keysS.get(), left.get(), lptab.get(), (int)n, (int)C.usable, B * L, derr.get());  // error flag read back with the proofs
     TB_CUDA(cudaMemcpyAsync(lpin.get(), keysA.get(), (size_t)B * L * n * 32, cudaMemcpyDeviceToDevice, st));
     fe_to_mont<Fp>(ctx, lpin.get(), (size_t)B * L * n);
     fe_to_mont<Fp>(ctx, lptab.get(), (size_t)B * L * n);
     for (int l = 0; l < L; ++l) {
-      prf_fill(ctx, seed, proof0, R_LK_IN_ROWS, (uint32_t)(l * (bf + 1)), lpin.get() + (size_t)l * n + C.usable, (long long)L * n, 1, bf + 1, B);
-      prf_fill(ctx, seed, proof0, R_LK_TAB_ROWS, (uint32_t)(l * (bf + 1)), lptab.get() + (size_t)l * n + C.usable, (long long)L * n, 1, bf + 1, B);
+      prf_fill(ctx, seed, proof0, R_LK_IN_ROWS, (uint32_t)(l * (bf + 1)), lpin.get() + (size_t)l * n + C.usable, (long long)L * nn, 1, bf + 1, B);
+      prf_fill(ctx, seed, proof0, R_LK_TAB_ROWS, (uint32_t)(l * (bf + 1)), lptab.get() + (size_t)l * n + C.usable, (long long)L * nn, 1, bf + 1, B);
     }
     prf_fill(ctx, seed, proof0, R_LK_IN_BLIND, 0, VP(V_LPIN_BLIND), NV, 1, L, B);
     prf_fill(ctx, seed, proof0, R_LK_TAB_BLIND, 0, VP(V_LPTAB_BLIND), NV, 1, L, B);
     // commit in transcript order: per lookup A' then S'
-    DevBuf<Fp> blinds(ctx, (size_t)B * L);
-    DevBuf<Aff<Fq>> pa(ctx, (size_t)B * L), ps(ctx, (size_t)B * L);
+    WBuf<Aff<Fq>> pa = ws.buf<Aff<Fq>>((size_t)B * L), ps = ws.buf<Aff<Fq>>((size_t)B * L);
     poly_copy(ctx, blinds.get(), L, VP(V_LPIN_BLIND), NV, L, B);
-    srs.commit(ctx, true, lpin.get(), (long long)n, B * L, blinds.get(), pa.get());
+    srs.commit(ctx, true, lpin.get(), nn, B * L, blinds.get(), pa.get());
     poly_copy(ctx, blinds.get(), L, VP(V_LPTAB_BLIND), NV, L, B);
-    srs.commit(ctx, true, lptab.get(), (long long)n, B * L, blinds.get(), ps.get());
+    srs.commit(ctx, true, lptab.get(), nn, B * L, blinds.get(), ps.get());
     for (int l = 0; l < L; ++l) { tr.points(pa.get() + l, L, 1, true); tr.points(ps.get() + l, L, 1, true); }
-    ntt_run<Fp>(ctx, k, true, lpin.get(), lpin_polys.get(), scratch.get(), B * L, (long long)n, (long long)n, nullptr, nullptr);
-    ntt_run<Fp>(ctx, k, true, lptab.get(), lptab_polys.get(), scratch.get(), B * L, (long long)n, (long long)n, nullptr, nullptr);
+    ntt_run<Fp>(ctx, k, true, lpin.get(), lpin_polys.get(), scratch.get(), B * L, nn, nn, nullptr, nullptr);
+    ntt_run<Fp>(ctx, k, true, lptab.get(), lptab_polys.get(), scratch.get(), B * L, nn, nn, nullptr, nullptr);
   }
   tr.squeeze(VP(V_BETA), NV, 1);
   tr.squeeze(VP(V_GAMMA), NV, 1);
 
   // ---- permutation grand products
-  DevBuf<Fp> pz_polys(ctx, (size_t)B * ns1 * n);
+  WBuf<Fp> pz_polys = ws.buf<Fp>((size_t)B * ns1 * n);
+  const size_t gp = (size_t)std::max(ns1, L1);
+  WBuf<Fp> gnum = ws.buf<Fp>((size_t)B * gp * n), gden = ws.buf<Fp>((size_t)B * gp * n), gz = ws.buf<Fp>((size_t)B * gp * n);
   if (nsets) {
-    DevBuf<Fp> num(ctx, (size_t)B * nsets * n), den(ctx, (size_t)B * nsets * n), z(ctx, (size_t)B * nsets * n);
     PermFrac pf; memset(&pf, 0, sizeof(pf));
-    pf.adv = adv_vals.get(); pf.adv_pstride = (long long)na * n; pf.inst = inst_vals.get(); pf.inst_pstride = (long long)ni1 * n; pf.fix = C.fixed_vals;
+    pf.adv = adv_vals.get(); pf.adv_pstride = (long long)na * nn; pf.inst = inst_vals.get(); pf.inst_pstride = (long long)ni1 * nn; pf.fix = C.fixed_vals;
     pf.sig = C.sig_vals; pf.perm_cols = C.d_perm; pf.P = P; pf.chunk = C.chunk; pf.nsets = nsets; pf.chal = vars.get(); pf.chal_stride = NV;
     pf.beta_slot = V_BETA; pf.gamma_slot = V_GAMMA; pf.delta = C.delta; pf.omega = C.omega; memcpy(pf.delta_c0, C.delta_c0, sizeof(pf.delta_c0));
-    pf.tw = ctx->tw_fp.fwd; pf.num = num.get(); pf.den = den.get(); pf.pstride = (long long)nsets * n; pf.n = (int)n; pf.k = k;
+    pf.tw = ctx->tw_fp.fwd; pf.num = gnum.get(); pf.den = gden.get(); pf.pstride = (long long)nsets * nn; pf.n = (int)n; pf.k = k;
     perm_fractions(ctx, pf, B);
-    batch_inverse(ctx, den.get(), (size_t)B * nsets * n);
-    vec_mul(ctx, num.get(), den.get(), (size_t)B * nsets * n);
-    prefix_product(ctx, z.get(), num.get(), (int)n, B * nsets);
-    perm_chain(ctx, z.get(), (long long)nsets * n, nsets, (int)n, (int)(n - bf - 1), B);
+    batch_inverse(ctx, gden.get(), (size_t)B * nsets * n);
+    vec_mul(ctx, gnum.get(), gden.get(), (size_t)B * nsets * n);
+    prefix_product(ctx, gz.get(), gnum.get(), (int)n, B * nsets);
+    perm_chain(ctx, gz.get(), (long long)nsets * nn, nsets, (int)n, (int)(n - bf - 1), B);
     for (int s = 0; s < nsets; ++s)
-      prf_fill(ctx, seed, proof0, R_PERM_ROWS, (uint32_t)(s * bf), z.get() + (size_t)s * n + (n - bf), (long long)nsets * n, 1, bf, B);
+      prf_fill(ctx, seed, proof0, R_PERM_ROWS, (uint32_t)(s * bf), gz.get() + (size_t)s * n + (n - bf), (long long)nsets * nn, 1, bf, B);
     prf_fill(ctx, seed, proof0, R_PERM_BLIND, 0, VP(V_PZ_BLIND), NV, 1, nsets, B);
-    DevBuf<Fp> blinds(ctx, (size_t)B * nsets);
     poly_copy(ctx, blinds.get(), nsets, VP(V_PZ_BLIND), NV, nsets, B);
-    srs.commit(ctx, true, z.get(), (long long)n, B * nsets, blinds.get(), pts.get());
+    srs.commit(ctx, true, gz.get(), nn, B * nsets, blinds.get(), pts.get());
     tr.points(pts.get(), nsets, nsets, true);
-    ntt_run<Fp>(ctx, k, true, z.get(), pz_polys.get(), scratch.get(), B * nsets, (long long)n, (long long)n, nullptr, nullptr);
+    ntt_run<Fp>(ctx, k, true, gz.get(), pz_polys.get(), scratch.get(), B * nsets, nn, nn, nullptr, nullptr);
   }
   // ---- lookup grand products
-  DevBuf<Fp> lz_polys(ctx, (size_t)B * L1 * n);
+  WBuf<Fp> lz_polys = ws.buf<Fp>((size_t)B * L1 * n);
   if (L) {
-    DevBuf<Fp> num(ctx, (size_t)B * L * n), den(ctx, (size_t)B * L * n), z(ctx, (size_t)B * L * n);
-    lookup_fractions(ctx, lkA.get(), lkS.get(), lpin.get(), lptab.get(), num.get(), den.get(), (long long)L * n, L, (int)n, vars.get(), NV, V_BETA, V_GAMMA, B);
-    batch_inverse(ctx, den.get(), (size_t)B * L * n);
-    vec_mul(ctx, num.get(), den.get(), (size_t)B * L * n);
-    prefix_product(ctx, z.get(), num.get(), (int)n, B * L);
+    lookup_fractions(ctx, lkA.get(), lkS.get(), lpin.get(), lptab.get(), gnum.get(), gden.get(), (long long)L * nn, L, (int)n, vars.get(), NV, V_BETA, V_GAMMA, B);
+    batch_inverse(ctx, gden.get(), (size_t)B * L * n);
+    vec_mul(ctx, gnum.get(), gden.get(), (size_t)B * L * n);
+    prefix_product(ctx, gz.get(), gnum.get(), (int)n, B * L);
     for (int l = 0; l < L; ++l)
-      prf_fill(ctx, seed, proof0, R_LKZ_ROWS, (uint32_t)(l * bf), z.get() + (size_t)l * n + (n - bf), (long long)L * n, 1, bf, B);
+      prf_fill(ctx, seed, proof0, R_LKZ_ROWS, (uint32_t)(l * bf), gz.get() + (size_t)l * n + (n - bf), (long long)L * nn, 1, bf, B);
     prf_fill(ctx, seed, proof0, R_LKZ_BLIND, 0, VP(V_LZ_BLIND), NV, 1, L, B);
-    DevBuf<Fp> blinds(ctx, (size_t)B * L);
     poly_copy(ctx, blinds.get(), L, VP(V_LZ_BLIND), NV, L, B);
-    srs.commit(ctx, true, z.get(), (long long)n, B * L, blinds.get(), pts.get());
+    srs.commit(ctx, true, gz.get(), nn, B * L, blinds.get(), pts.get());
     tr.points(pts.get(), L, L, true);
-    ntt_run<Fp>(ctx, k, true, z.get(), lz_polys.get(), scratch.get(), B * L, (long long)n, (long long)n, nullptr, nullptr);
+    ntt_run<Fp>(ctx, k, true, gz.get(), lz_polys.get(), scratch.get(), B * L, nn, nn, nullptr, nullptr);
   }
   // ---- vanishing argument: random polynomial
-  DevBuf<Fp> random_poly(ctx, (size_t)B * n);
-  prf_fill(ctx, seed, proof0, R_RANDOM_POLY, 0, random_poly.get(), (long long)n, 1, (int)n, B);
+  WBuf<Fp> random_poly = ws.buf<Fp>((size_t)B * n);
+  prf_fill(ctx, seed, proof0, R_RANDOM_POLY, 0, random_poly.get(), nn, 1, (int)n, B);
   prf_fill(ctx, seed, proof0, R_RANDOM_BLIND, 0, VP(V_RANDOM_BLIND), NV, 1, 1, B);
-  { DevBuf<Fp> blinds(ctx, B); poly_copy(ctx, blinds.get(), 1, VP(V_RANDOM_BLIND), NV, 1, B);
-    srs.commit(ctx, false, random_poly.get(), (long long)n, B, blinds.get(), pts.get()); }
+  poly_copy(ctx, blinds.get(), 1, VP(V_RANDOM_BLIND), NV, 1, B);
+  srs.commit(ctx, false, random_poly.get(), nn, B, blinds.get(), pts.get());
   tr.points(pts.get(), 1, 1, true);
   tr.squeeze(VP(V_Y), NV, 1);
 
   // ---- quotient, tiled by sub-coset
   const int R = C.R;
-  DevBuf<Fp> hext(ctx, (size_t)B * R * n), hcoef(ctx, (size_t)B * C.pieces * n);
-  { DevBuf<Fp> c_adv(ctx, (size_t)B * na * n), c_inst(ctx, (size_t)B * ni1 * n), c_pz(ctx, (size_t)B * ns1 * n), c_lz(ctx, (size_t)B * L1 * n),
-        c_lpin(ctx, (size_t)B * L1 * n), c_lptab(ctx, (size_t)B * L1 * n), c_lkA(ctx, (size_t)B * L1 * n), c_lkS(ctx, (size_t)B * L1 * n), gate(ctx, (size_t)B * n);
+  WBuf<Fp> hext = ws.buf<Fp>((size_t)B * R * n), hcoef = ws.buf<Fp>((size_t)B * C.pieces * n);
+  { WBuf<Fp> c_adv = ws.buf<Fp>((size_t)B * na * n), c_inst = ws.buf<Fp>((size_t)B * ni1 * n), c_pz = ws.buf<Fp>((size_t)B * ns1 * n), c_lz = ws.buf<Fp>((size_t)B * L1 * n),
+        c_lpin = ws.buf<Fp>((size_t)B * L1 * n), c_lptab = ws.buf<Fp>((size_t)B * L1 * n), c_lkA = ws.buf<Fp>((size_t)B * L1 * n), c_lkS = ws.buf<Fp>((size_t)B * L1 * n),
+        gate = ws.buf<Fp>((size_t)B * n), V = ws.buf<Fp>((size_t)B * R * n);
     for (int k1 = 0; k1 < R; ++k1) {
       NttHook<Fp> h = coset_hook(C, k1, false);
-      ntt_run<Fp>(ctx, k, false, adv_polys.get(), c_adv.get(), scratch.get(), B * na, (long long)n, (long long)n, &h, nullptr);
-      if (ni) ntt_run<Fp>(ctx, k, false, inst_polys.get(), c_inst.get(), scratch.get(), B * ni, (long long)n, (long long)n, &h, nullptr);
-      if (nsets) ntt_run<Fp>(ctx, k, false, pz_polys.get(), c_pz.get(), scratch.get(), B * nsets, (long long)n, (long long)n, &h, nullptr);
+      ntt_run<Fp>(ctx, k, false, adv_polys.get(), c_adv.get(), scratch.get(), B * na, nn, nn, &h, nullptr);
+      if (ni) ntt_run<Fp>(ctx, k, false, inst_polys.get(), c_inst.get(), scratch.get(), B * ni, nn, nn, &h, nullptr);
+      if (nsets) ntt_run<Fp>(ctx, k, false, pz_polys.get(), c_pz.get(), scratch.get(), B * nsets, nn, nn, &h, nullptr);
       if (L) {
-        ntt_run<Fp>(ctx, k, false, lz_polys.get(), c_lz.get(), scratch.get(), B * L, (long long)n, (long long)n, &h, nullptr);
-        ntt_run<Fp>(ctx, k, false, lpin_polys.get(), c_lpin.get(), scratch.get(), B * L, (long long)n, (long long)n, &h, nullptr);
-        ntt_run<Fp>(ctx, k, false, lptab_polys.get(), c_lptab.get(), scratch.get(), B * L, (long long)n, (long long)n, &h, nullptr);
+        ntt_run<Fp>(ctx, k, false, lz_polys.get(), c_lz.get(), scratch.get(), B * L, nn, nn, &h, nullptr);
+        ntt_run<Fp>(ctx, k, false, lpin_polys.get(), c_lpin.get(), scratch.get(), B * L, nn, nn, &h, nullptr);
+        ntt_run<Fp>(ctx, k, false, lptab_polys.get(), c_lptab.get(), scratch.get(), B * L, nn, nn, &h, nullptr);
       }
-      qd.adv = c_adv.get(); qd.adv_pstride = (long long)na * n; qd.inst = c_inst.get(); qd.inst_pstride = (long long)ni1 * n;
+      qd.adv = c_adv.get(); qd.adv_pstride = (long long)na * nn; qd.inst = c_inst.get(); qd.inst_pstride = (long long)ni1 * nn;
       qd.fix = C.fixed_cosets; qd.R = R; qd.k1 = k1; qd.lkA = c_lkA.get(); qd.lkS = c_lkS.get();
-      qd.gate_out = gate.get(); qd.gate_pstride = (long long)n;
+      qd.gate_out = gate.get(); qd.gate_pstride = nn;
       q_run(ctx, C.prog_gates, qd, B);
       if (L) { qd.gate_out = nullptr; q_run(ctx, C.prog_lookups, qd, B); }
       QFinish f; memset(&f, 0, sizeof(f));
-      f.gate = gate.get(); f.adv = c_adv.get(); f.adv_pstride = (long long)na * n; f.inst = c_inst.get(); f.inst_pstride = (long long)ni1 * n;
+      f.gate = gate.get(); f.adv = c_adv.get(); f.adv_pstride = (long long)na * nn; f.inst = c_inst.get(); f.inst_pstride = (long long)ni1 * nn;
       f.fix = C.fixed_cosets; f.sig = C.sig_cosets; f.R = R; f.k1 = k1; f.l0 = C.l0; f.l_last = C.l_last; f.l_blind = C.l_blind;
-      f.pz = c_pz.get(); f.pz_pstride = (long long)ns1 * n; f.lz = c_lz.get(); f.lpin = c_lpin.get(); f.lptab = c_lptab.get(); f.lk_pstride = (long long)L1 * n;
+      f.pz = c_pz.get(); f.pz_pstride = (long long)ns1 * nn; f.lz = c_lz.get(); f.lpin = c_lpin.get(); f.lptab = c_lptab.get(); f.lk_pstride = (long long)L1 * nn;
       f.lkA = c_lkA.get(); f.lkS = c_lkS.get(); f.perm_cols = C.d_perm; f.P = P; f.chunk = C.chunk; f.nsets = nsets; f.L = L; f.bf = bf;
       f.chal = vars.get(); f.chal_stride = NV; f.y_slot = V_Y; f.beta_slot = V_BETA; f.gamma_slot = V_GAMMA;
       f.delta = C.delta; f.zeta = C.zeta; f.t_inv = C.t_inv[k1]; memcpy(f.delta_c0, C.delta_c0, sizeof(f.delta_c0)); f.tw = ctx->tw_fp.fwd;
-      f.ext_k = C.ext_k; f.k = k; f.out = hext.get(); f.out_pstride = (long long)R * n; f.n = (int)n;
+      f.ext_k = C.ext_k; f.k = k; f.out = hext.get(); f.out_pstride = (long long)R * nn; f.n = (int)n;
       q_finish(ctx, f, B);
     }
     // extended_to_coeff: per sub-coset iNTT with w_ext^(-i*k1) (step A), then the size-R cross transform (step B)
-    DevBuf<Fp> V(ctx, (size_t)B * R * n);
     for (int k1 = 0; k1 < R; ++k1) {
       NttHook<Fp> h = coset_hook(C, k1, true);
-      ntt_run<Fp>(ctx, k, true, hext.get() + (size_t)k1 * n, V.get() + (size_t)k1 * n, scratch.get(), B, (long long)R * n, (long long)R * n, nullptr, &h);
+      ntt_run<Fp>(ctx, k, true, hext.get() + (size_t)k1 * n, V.get() + (size_t)k1 * n, scratch.get(), B, (long long)R * nn, (long long)R * nn, nullptr, &h);
     }
-    h_cross(ctx, V.get(), (long long)R * n, hcoef.get(), (long long)C.pieces * n, (int)n, R, (int)C.pieces, C.wr_inv, C.r_inv, C.zeta.sqr(), B);
+    h_cross(ctx, V.get(), (long long)R * nn, hcoef.get(), (long long)C.pieces * nn, (int)n, R, (int)C.pieces, C.wr_inv, C.r_inv, C.zeta.sqr(), B);
   }
   prf_fill(ctx, seed, proof0, R_H_BLIND, 0, VP(V_H_BLINDS), NV, 1, (int)C.pieces, B);
-  { DevBuf<Fp> blinds(ctx, (size_t)B * C.pieces);
-    poly_copy(ctx, blinds.get(), C.pieces, VP(V_H_BLINDS), NV, C.pieces, B);
-    srs.commit(ctx, false, hcoef.get(), (long long)n, B * (int)C.pieces, blinds.get(), pts.get()); }
+  poly_copy(ctx, blinds.get(), C.pieces, VP(V_H_BLINDS), NV, C.pieces, B);
+  srs.commit(ctx, false, hcoef.get(), nn, B * (int)C.pieces, blinds.get(), pts.get());
   tr.points(pts.get(), C.pieces, C.pieces, true);
   tr.squeeze(VP(V_X), NV, 1);
 
   // ---- evaluation points, h(X) = sum xn^i h_i, blinds
-  DevBuf<Fp> h_poly(ctx, (size_t)B * n);
+  WBuf<Fp> h_poly = ws.buf<Fp>((size_t)B * n);
   { Prog p;
     p.op(S_POW2K, V_XN, V_X, 0, (uint32_t)k);
     for (size_t i = 0; i < C.rots.size(); ++i) {
@@ -462,11 +496,10 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
     p.op(S_SUB, V_H_BLIND, V_H_BLIND, V_H_BLIND);
     for (int i = (int)C.pieces - 1; i >= 0; --i) p.op(S_FMA, V_H_BLIND, V_XN, V_H_BLINDS + i);
     run_prog(p); }
-  TB_CUDA(cudaMemsetAsync(h_poly.get(), 0, (size_t)B * n * 32, st));
-  for (int i = (int)C.pieces - 1; i >= 0; --i) poly_fma(ctx, h_poly.get(), (long long)n, VP(V_XN), NV, hcoef.get() + (size_t)i * n, (long long)C.pieces * n, (int)n, B);
+  h_poly.zero();
+  for (int i = (int)C.pieces - 1; i >= 0; --i) poly_fma(ctx, h_poly.get(), nn, VP(V_XN), NV, hcoef.get() + (size_t)i * n, (long long)C.pieces * nn, (int)n, B);
 
   auto rot_slot = [&](int rot) { return V_PT + (int)(std::find(C.rots.begin(), C.rots.end(), rot) - C.rots.begin()); };
-  const long long nn = (long long)n;
   auto mk_item = [](const Fp* base, long long bstride, int point) { EvalItem it; it.base = base; it.bstride = bstride; it.point = point; it.pad = 0; return it; };
   struct PRef { const Fp* base; long long bstride; int blind_slot; };
   auto poly_ref = [&](const PolyId& id) -> PRef {
@@ -485,120 +518,114 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   };
   { std::vector<EvalItem> items;
     for (auto& e : C.evals) { PRef r = poly_ref(e.poly); items.push_back(mk_item(r.base, r.bstride, rot_slot(e.rot))); }
-    DevBuf<EvalItem> ditems(ctx, items.size()); ditems.upload(items.data(), items.size()); ctx->sync();
-    DevBuf<Fp> ev(ctx, (size_t)B * items.size());
-    poly_eval(ctx, ditems.get(), (int)items.size(), vars.get(), NV, ev.get(), (long long)items.size(), (int)n, B);
+    const EvalItem* ditems = reinterpret_cast<const EvalItem*>(cached_upload(items.data(), items.size() * sizeof(EvalItem)));
+    WBuf<Fp> ev = ws.buf<Fp>((size_t)B * items.size());
+    poly_eval(ctx, ditems, (int)items.size(), vars.get(), NV, ev.get(), (long long)items.size(), (int)n, B);
     tr.scalars(ev.get(), (long long)items.size(), (int)items.size(), true); }
 
   // ---- multiopen
   tr.squeeze(VP(V_X1), NV, 1);
   tr.squeeze(VP(V_X2), NV, 1);
-  DevBuf<Fp> q_polys(ctx, (size_t)B * nps * n), q_prime(ctx, (size_t)B * n), kd_a(ctx, (size_t)B * n), kd_b(ctx, (size_t)B * n);
+  WBuf<Fp> q_polys = ws.buf<Fp>((size_t)B * nps * n), q_prime = ws.buf<Fp>((size_t)B * n), kd_a = ws.buf<Fp>((size_t)B * n), kd_b = ws.buf<Fp>((size_t)B * n);
   { std::vector<char> started(nps, 0); Prog p;
     for (int s = 0; s < nps; ++s) p.op(S_SUB, V_QBLIND + s, V_QBLIND + s, V_QBLIND + s);
     for (size_t c = 0; c < C.uniq.size(); ++c) {
       PRef r = poly_ref(C.uniq[c]); int s = C.uniq_set[c];
       Fp* q = q_polys.get() + (size_t)s * n;
-      if (!started[s]) { poly_copy(ctx, q, (long long)nps * n, r.base, r.bstride, (int)n, B); started[s] = 1; }
-      else poly_fma(ctx, q, (long long)nps * n, VP(V_X1), NV, r.base, r.bstride, (int)n, B);
+      if (!started[s]) { poly_copy(ctx, q, (long long)nps * nn, r.base, r.bstride, (int)n, B); started[s] = 1; }
+      else poly_fma(ctx, q, (long long)nps * nn, VP(V_X1), NV, r.base, r.bstride, (int)n, B);
       p.op(S_FMA, V_QBLIND + s, V_X1, r.blind_slot);
     }
     run_prog(p); }
   for (int s = 0; s < nps; ++s) {
-    const Fp* cur = q_polys.get() + (size_t)s * n; long long cur_stride = (long long)nps * n;
+    const Fp* cur = q_polys.get() + (size_t)s * n; long long cur_stride = (long long)nps * nn;
     Fp* bufs[2] = {kd_a.get(), kd_b.get()}; int w = 0;
     for (int rot : C.point_sets[s]) {
-      poly_kate_div(ctx, bufs[w], (long long)n, cur, cur_stride, VP(rot_slot(rot)), NV, (int)n, B);
-      cur = bufs[w]; cur_stride = (long long)n; w ^= 1;
+      poly_kate_div(ctx, bufs[w], nn, cur, cur_stride, VP(rot_slot(rot)), NV, (int)n, B);
+      cur = bufs[w]; cur_stride = nn; w ^= 1;
     }
-    if (s == 0) poly_copy(ctx, q_prime.get(), (long long)n, cur, cur_stride, (int)n, B);
-    else poly_fma(ctx, q_prime.get(), (long long)n, VP(V_X2), NV, cur, cur_stride, (int)n, B);
+    if (s == 0) poly_copy(ctx, q_prime.get(), nn, cur, cur_stride, (int)n, B);
+    else poly_fma(ctx, q_prime.get(), nn, VP(V_X2), NV, cur, cur_stride, (int)n, B);
   }
   prf_fill(ctx, seed, proof0, R_QPRIME_BLIND, 0, VP(V_QPRIME_BLIND), NV, 1, 1, B);
-  { DevBuf<Fp> blinds(ctx, B); poly_copy(ctx, blinds.get(), 1, VP(V_QPRIME_BLIND), NV, 1, B);
-    srs.commit(ctx, false, q_prime.get(), (long long)n, B, blinds.get(), pts.get()); }
+  poly_copy(ctx, blinds.get(), 1, VP(V_QPRIME_BLIND), NV, 1, B);
+  srs.commit(ctx, false, q_prime.get(), nn, B, blinds.get(), pts.get());
   tr.points(pts.get(), 1, 1, true);
   tr.squeeze(VP(V_X3), NV, 1);
   { std::vector<EvalItem> items;
     for (int s = 0; s < nps; ++s) items.push_back(mk_item(q_polys.get() + (size_t)s * n, (long long)nps * nn, V_X3));
-    DevBuf<EvalItem> ditems(ctx, items.size()); ditems.upload(items.data(), items.size()); ctx->sync();
-    DevBuf<Fp> ev(ctx, (size_t)B * nps);
-    poly_eval(ctx, ditems.get(), nps, vars.get(), NV, ev.get(), nps, (int)n, B);
+    const EvalItem* ditems = reinterpret_cast<const EvalItem*>(cached_upload(items.data(), items.size() * sizeof(EvalItem)));
+    WBuf<Fp> ev = ws.buf<Fp>((size_t)B * nps);
+    poly_eval(ctx, ditems, nps, vars.get(), NV, ev.get(), nps, (int)n, B);
     tr.scalars(ev.get(), nps, nps, true); }
   tr.squeeze(VP(V_X4), NV, 1);
   // p(X) = ((q' x4 + q_0) x4 + q_1) ... ; same for the blinds
-  DevBuf<Fp> pprime(ctx, (size_t)B * n), bvec(ctx, (size_t)B * n), s_poly(ctx, (size_t)B * n);
+  WBuf<Fp> pprime = ws.buf<Fp>((size_t)B * n), bvec = ws.buf<Fp>((size_t)B * n), s_poly = ws.buf<Fp>((size_t)B * n);
   Fp* p_poly = q_prime.get();
   { Prog p; p.op(S_COPY, V_P_BLIND, V_QPRIME_BLIND);
-    for (int s = 0; s < nps; ++s) { poly_fma(ctx, p_poly, (long long)n, VP(V_X4), NV, q_polys.get() + (size_t)s * n, (long long)nps * n, (int)n, B); p.op(S_FMA, V_P_BLIND, V_X4, V_QBLIND + s); }
+    for (int s = 0; s < nps; ++s) { poly_fma(ctx, p_poly, nn, VP(V_X4), NV, q_polys.get() + (size_t)s * n, (long long)nps * nn, (int)n, B); p.op(S_FMA, V_P_BLIND, V_X4, V_QBLIND + s); }
     run_prog(p); }
 
-  // ---- inner product argument (poly/commitment/prover.rs)
-  prf_fill(ctx, seed, proof0, R_S_POLY, 0, s_poly.get(), (long long)n, 1, (int)n, B);
+  // ---- inner product argument (poly/commitment/prover.rs), s-vector form
+  prf_fill(ctx, seed, proof0, R_S_POLY, 0, s_poly.get(), nn, 1, (int)n, B);
   prf_fill(ctx, seed, proof0, R_S_BLIND, 0, VP(V_S_BLIND), NV, 1, 1, B);
-  DevBuf<EvalItem> one_item(ctx, 1);
   auto eval_one = [&](const Fp* poly, int out_slot) {
     EvalItem it = mk_item(poly, nn, V_X3);
-    one_item.upload(&it, 1); ctx->sync();
-    poly_eval(ctx, one_item.get(), 1, vars.get(), NV, VP(out_slot), NV, (int)n, B);
+    const EvalItem* d = reinterpret_cast<const EvalItem*>(cached_upload(&it, sizeof(it)));
+    poly_eval(ctx, d, 1, vars.get(), NV, VP(out_slot), NV, (int)n, B);
   };
   eval_one(s_poly.get(), V_S_AT);
-  poly_add_at(ctx, s_poly.get(), (long long)n, 0, VP(V_S_AT), NV, -1, B);
-  { DevBuf<Fp> blinds(ctx, B); poly_copy(ctx, blinds.get(), 1, VP(V_S_BLIND), NV, 1, B);
-    srs.commit(ctx, false, s_poly.get(), (long long)n, B, blinds.get(), pts.get()); }
+  poly_add_at(ctx, s_poly.get(), nn, 0, VP(V_S_AT), NV, -1, B);
+  poly_copy(ctx, blinds.get(), 1, VP(V_S_BLIND), NV, 1, B);
+  srs.commit(ctx, false, s_poly.get(), nn, B, blinds.get(), pts.get());
   tr.points(pts.get(), 1, 1, true);
   tr.squeeze(VP(V_XI), NV, 1);
   tr.squeeze(VP(V_Z), NV, 1);
-  poly_copy(ctx, pprime.get(), (long long)n, s_poly.get(), (long long)n, (int)n, B);
-  poly_fma(ctx, pprime.get(), (long long)n, VP(V_XI), NV, p_poly, (long long)n, (int)n, B);
+  poly_copy(ctx, pprime.get(), nn, s_poly.get(), nn, (int)n, B);
+  poly_fma(ctx, pprime.get(), nn, VP(V_XI), NV, p_poly, nn, (int)n, B);
   eval_one(pprime.get(), V_V);
-  poly_add_at(ctx, pprime.get(), (long long)n, 0, VP(V_V), NV, -1, B);
+  poly_add_at(ctx, pprime.get(), nn, 0, VP(V_V), NV, -1, B);
   { Prog p; p.op(S_MUL, V_F, V_S_BLIND, V_XI); p.op(S_ADD, V_F, V_F, V_P_BLIND); run_prog(p); }
-  powers(ctx, bvec.get(), (long long)n, VP(V_X3), NV, (int)n, B);
-  DevBuf<Aff<Fq>> gprime(ctx, (size_t)B * n);
-  poly_copy(ctx, reinterpret_cast<Fp*>(gprime.get()), 2 * nn, reinterpret_cast<const Fp*>(srs.g), 0, (int)(2 * n), B);  // Aff<Fq> = 2 x 32 bytes
-  DevBuf<Xyzz<Fq>> accL(ctx, B), accR(ctx, B);
-  DevBuf<Aff<Fq>> ptL(ctx, B), ptR(ctx, B);
-  DevBuf<Fp> ex(ctx, (size_t)B * 2);
-  DevBuf<int> dslots(ctx, 4);
+  powers(ctx, bvec.get(), nn, VP(V_X3), NV, (int)n, B);
+  WBuf<Fp> sfull = ws.buf<Fp>((size_t)B * n), cLR = ws.buf<Fp>((size_t)B * 2 * n), ex = ws.buf<Fp>((size_t)B * 4);
+  WBuf<Xyzz<Fq>> accLR = ws.buf<Xyzz<Fq>>((size_t)B * 2);
+  WBuf<Aff<Fq>> ptLR = ws.buf<Aff<Fq>>((size_t)B * 2);
+  fill_const_kernel<<<(unsigned)(((size_t)B * n + 255) / 256), 256, 0, st>>>(sfull.get(), (size_t)B * n, Fp::one());
+  Prog round_prog;  // identical every round
+  round_prog.op(S_INV, V_UINV, V_U); round_prog.op(S_MUL, V_T0, V_LR, V_UINV); round_prog.op(S_ADD, V_F, V_F, V_T0);
+  round_prog.op(S_MUL, V_T0, V_RR, V_U); round_prog.op(S_ADD, V_F, V_F, V_T0);
+  const ScalarInstr* d_round = reinterpret_cast<const ScalarInstr*>(cached_upload(round_prog.ins.data(), round_prog.ins.size() * sizeof(ScalarInstr)));
   for (int j = 0; j < k; ++j) {
-    int half = (int)(n >> (j + 1));
-    MsmConfig cfg;
-    msm_run<Fq, Fp>(ctx, pprime.get() + half, (long long)n, gprime.get(), (long long)n, half, B, cfg, accL.get());
-    msm_run<Fq, Fp>(ctx, pprime.get(), (long long)n, gprime.get() + half, (long long)n, half, B, cfg, accR.get());
-    inner_product(ctx, VP(V_VL), NV, pprime.get() + half, (long long)n, bvec.get(), (long long)n, half, B);
-    inner_product(ctx, VP(V_VR), NV, pprime.get(), (long long)n, bvec.get() + half, (long long)n, half, B);
+    int m = (int)(n >> j), half = m >> 1;
+    { ProfScope fold_scope(ctx, PC_IPA_FOLD);
+      ipa_round_scalars_kernel<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, st>>>(pprime.get(), sfull.get(), cLR.get(), (int)n, m); }
+    inner_product(ctx, VP(V_VL), NV, pprime.get() + half, nn, bvec.get(), nn, half, B);
+    inner_product(ctx, VP(V_VR), NV, pprime.get(), nn, bvec.get() + half, nn, half, B);
     prf_fill(ctx, seed, proof0, R_IPA_L, (uint32_t)j, VP(V_LR), NV, 1, 1, B);
     prf_fill(ctx, seed, proof0, R_IPA_R, (uint32_t)j, VP(V_RR), NV, 1, 1, B);
-    { Prog p; p.op(S_MUL, V_VLZ, V_VL, V_Z); p.op(S_MUL, V_VRZ, V_VR, V_Z); run_prog(p); }
-    // L = accL + lr * w + (vl z) * u   (srs.wu = {w, u})
-    int slotsL[2] = {V_LR, V_VLZ}, slotsR[2] = {V_RR, V_VRZ};
-    TB_CUDA(cudaMemcpyAsync(dslots.get(), slotsL, 8, cudaMemcpyHostToDevice, st));
-    TB_CUDA(cudaMemcpyAsync(dslots.get() + 2, slotsR, 8, cudaMemcpyHostToDevice, st));
-    ctx->sync();
-    gather_vars_kernel<<<(B * 2 + 63) / 64, 64, 0, st>>>(ex.get(), 2, vars.get(), NV, dslots.get(), 2, B);
-    points_finalize<Fq, Fp>(ctx, accL.get(), B, ex.get(), srs.wu, 2, ptL.get());
-    gather_vars_kernel<<<(B * 2 + 63) / 64, 64, 0, st>>>(ex.get(), 2, vars.get(), NV, dslots.get() + 2, 2, B);
-    points_finalize<Fq, Fp>(ctx, accR.get(), B, ex.get(), srs.wu, 2, ptR.get());
-    tr.points(ptL.get(), 1, 1, true);
-    tr.points(ptR.get(), 1, 1, true);
+    ipa_extras_kernel<<<(B + 31) / 32, 32, 0, st>>>(ex.get(), vars.get(), NV, V_LR, V_RR, V_VL, V_VR, V_Z, B);
+    // L_j, R_j = <cL | cR, g> + l_rand * w + (value * z) * u : one batched fixed-base MSM, K = 2 per proof
+    srs.commit_xyzz(ctx, false, cLR.get(), nn, 2 * B, ex.get(), 2, accLR.get());
+    points_to_affine<Fq>(ctx, accLR.get(), 2 * B, ptLR.get());
+    tr.points(ptLR.get(), 2, 2, true);
     tr.squeeze(VP(V_U), NV, 1);
-    { Prog p; p.op(S_INV, V_UINV, V_U); p.op(S_MUL, V_T0, V_LR, V_UINV); p.op(S_ADD, V_F, V_F, V_T0); p.op(S_MUL, V_T0, V_RR, V_U); p.op(S_ADD, V_F, V_F, V_T0); run_prog(p); }
-    ProfScope fold_scope(ctx, PC_IPA_FOLD);
-    ipa_fold_g_kernel<<<dim3((half + 63) / 64, B), 64, 0, st>>>(gprime.get(), (long long)n, half, vars.get(), NV, V_U);
-    TB_LAUNCH_CHECK();
-    ipa_fold_scalars_kernel<<<dim3((half + 127) / 128, B), 128, 0, st>>>(pprime.get(), bvec.get(), (long long)n, half, vars.get(), NV, V_U, V_UINV);
-    TB_LAUNCH_CHECK(); ctx->launches += 4;
+    scalar_program(ctx, vars.get(), NV, d_round, (int)round_prog.ins.size(), dconsts, B);
+    { ProfScope fold_scope(ctx, PC_IPA_FOLD);
+      ipa_fold_kernel<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, st>>>(pprime.get(), bvec.get(), sfull.get(), (int)n, half, vars.get(), NV, V_U, V_UINV); }
+    TB_LAUNCH_CHECK(); ctx->launches += 3;
   }
-  poly_copy(ctx, VP(V_C), NV, pprime.get(), (long long)n, 1, B);
+  poly_copy(ctx, VP(V_C), NV, pprime.get(), nn, 1, B);
   tr.scalars(VP(V_C), NV, 1, true);
   tr.scalars(VP(V_F), NV, 1, true);
 
-  // ---- download
+  // ---- download (the only host synchronisation of the call)
   std::vector<TrState> hst(B);
+  uint32_t herr = 0;
   TB_CUDA(cudaMemcpyAsync(hst.data(), tr.states.get(), (size_t)B * sizeof(TrState), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(&herr, derr.get(), 4, cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaMemcpy2DAsync(proofs_out, proof_stride, tr.proofs.get(), C.proof_len, C.proof_len, B, cudaMemcpyDeviceToHost, st));
   ctx->sync();
+  if (herr) throw ConstraintError("lookup input not contained in the table (ConstraintSystemFailure)");
   for (int b = 0; b < B; ++b) {
     if (hst[b].error & TR_ERR_INFINITY) throw std::runtime_error("cannot write points at infinity to the transcript");
     if (hst[b].error || hst[b].proof_len != C.proof_len) throw std::runtime_error("internal error: proof length mismatch");

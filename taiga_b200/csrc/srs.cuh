@@ -13,8 +13,8 @@ struct Srs {
   int c = 16, W = 16;                       // fixed-base window bits / number of table windows
   Aff<Fq>* g = nullptr;                      // [n]   (device, Montgomery)
   Aff<Fq>* g_lagrange = nullptr;             // [n]
-  Aff<Fq>* tab_g = nullptr;                  // [W][n]  2^(c*w) * g[i]
-  Aff<Fq>* tab_gl = nullptr;                 // [W][n]
+  Aff<Fq>* tab_g = nullptr;                  // [W][n+2]  2^(c*w) * {g[0..n), w, u}
+  Aff<Fq>* tab_gl = nullptr;                 // [W][n+2]  same with g_lagrange
   Aff<Fq>* wu = nullptr;                     // [2] = {w, u}
   Aff<Fq> w_host, u_host;                    // Montgomery
 
@@ -27,8 +27,8 @@ struct Srs {
     try {
       TB_CUDA(cudaMalloc(&s->g, n * sizeof(Aff<Fq>)));
       TB_CUDA(cudaMalloc(&s->g_lagrange, n * sizeof(Aff<Fq>)));
-      TB_CUDA(cudaMalloc(&s->tab_g, (size_t)s->W * n * sizeof(Aff<Fq>)));
-      TB_CUDA(cudaMalloc(&s->tab_gl, (size_t)s->W * n * sizeof(Aff<Fq>)));
+      TB_CUDA(cudaMalloc(&s->tab_g, (size_t)s->W * (n + 2) * sizeof(Aff<Fq>)));
+      TB_CUDA(cudaMalloc(&s->tab_gl, (size_t)s->W * (n + 2) * sizeof(Aff<Fq>)));
       TB_CUDA(cudaMalloc(&s->wu, 2 * sizeof(Aff<Fq>)));
       TB_CUDA(cudaMemcpyAsync(s->g, g, n * 64, cudaMemcpyHostToDevice, ctx->stream));
       TB_CUDA(cudaMemcpyAsync(s->g_lagrange, gl, n * 64, cudaMemcpyHostToDevice, ctx->stream));
@@ -37,8 +37,14 @@ struct Srs {
       fe_to_mont<Fq>(ctx, reinterpret_cast<Fq*>(s->g), 2 * n);
       fe_to_mont<Fq>(ctx, reinterpret_cast<Fq*>(s->g_lagrange), 2 * n);
       fe_to_mont<Fq>(ctx, reinterpret_cast<Fq*>(s->wu), 4);
-      msm_build_tables<Fq>(ctx, s->g, (int)n, c, s->W, s->tab_g);
-      msm_build_tables<Fq>(ctx, s->g_lagrange, (int)n, c, s->W, s->tab_gl);
+      { // window 0 of each table: the basis followed by w and u (the extra terms every commitment / IPA round adds)
+        DevBuf<Aff<Fq>> b0(ctx, n + 2);
+        for (int t = 0; t < 2; ++t) {
+          TB_CUDA(cudaMemcpyAsync(b0.get(), t ? s->g_lagrange : s->g, n * sizeof(Aff<Fq>), cudaMemcpyDeviceToDevice, ctx->stream));
+          TB_CUDA(cudaMemcpyAsync(b0.get() + n, s->wu, 2 * sizeof(Aff<Fq>), cudaMemcpyDeviceToDevice, ctx->stream));
+          msm_build_tables<Fq>(ctx, b0.get(), (int)n + 2, c, s->W, t ? s->tab_gl : s->tab_g);
+        }
+      }
       Aff<Fq> h[2];
       TB_CUDA(cudaMemcpyAsync(h, s->wu, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
       ctx->sync();
@@ -48,16 +54,16 @@ struct Srs {
   }
   ~Srs() { cudaFree(g); cudaFree(g_lagrange); cudaFree(tab_g); cudaFree(tab_gl); cudaFree(wu); }
 
-  // acc[k] = MSM(scalars_k, basis) via the fixed-base tables (no blinding term, no normalisation)
-  void commit_xyzz(Ctx* c_, bool lagrange, const Fp* scalars, long long stride, int K, Xyzz<Fq>* acc) const {
-    MsmConfig cfg; cfg.c = c; cfg.table_windows = W;
+  // acc[k] = MSM(scalars_k, basis) + sum_j extras[k][j] * {w, u}[j] via the fixed-base tables (no normalisation)
+  void commit_xyzz(Ctx* c_, bool lagrange, const Fp* scalars, long long stride, int K, const Fp* extras, int n_extra, Xyzz<Fq>* acc) const {
+    MsmConfig cfg; cfg.c = c; cfg.table_windows = W; cfg.table_stride = (int)n + 2; cfg.n_extra = extras ? n_extra : 0; cfg.extra_scalars = extras;
     msm_run<Fq, Fp>(c_, scalars, stride, lagrange ? tab_gl : tab_g, 0, (int)n, K, cfg, acc);
   }
-  // out[k] = affine(MSM(scalars_k, basis) + blinds[k] * w)
+  // out[k] = affine(MSM(scalars_k, basis) + blinds[k] * w)      (Params::commit / commit_lagrange)
   void commit(Ctx* c_, bool lagrange, const Fp* scalars, long long stride, int K, const Fp* blinds, Aff<Fq>* out) const {
     DevBuf<Xyzz<Fq>> acc(c_, K);
-    commit_xyzz(c_, lagrange, scalars, stride, K, acc.get());
-    points_finalize<Fq, Fp>(c_, acc.get(), K, blinds, wu, blinds ? 1 : 0, out);
+    commit_xyzz(c_, lagrange, scalars, stride, K, blinds, 1, acc.get());
+    points_to_affine<Fq>(c_, acc.get(), K, out);
   }
 };
 
