@@ -10,7 +10,7 @@ namespace tb {
 struct Srs {
   Ctx* ctx = nullptr;
   uint32_t k = 0; size_t n = 0;
-  int c = 16, W = 16;                       // fixed-base window bits / number of table windows
+  int c = 13, W = 20;                       // fixed-base window bits / number of table windows
   Aff<Fq>* g = nullptr;                      // [n]   (device, Montgomery)
   Aff<Fq>* g_lagrange = nullptr;             // [n]
   Aff<Fq>* tab_g = nullptr;                  // [W][n+2]  2^(c*w) * {g[0..n), w, u}
@@ -21,7 +21,7 @@ struct Srs {
   static Srs* load(Ctx* ctx, uint32_t k, const uint8_t* g, const uint8_t* gl, const uint8_t* w, const uint8_t* u) {
     Srs* s = new Srs();
     s->ctx = ctx; s->k = k; s->n = size_t(1) << k;
-    int c = (int)k + 1; if (c < 4) c = 4; if (c > 16) c = 16;
+    int c = (int)k - 2; if (c < 4) c = 4; if (c > 13) c = 13;  // 13: 4096 buckets per MSM at k = 15 (see msm.cu MSM_FIXED_C)
     s->c = c; s->W = (256 + c - 1) / c;
     size_t n = s->n;
     try {
