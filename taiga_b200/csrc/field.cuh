@@ -44,6 +44,53 @@ struct FqParams {  // Vesta base field = Pallas scalar field
   static constexpr int id = 1;
 };
 
+
+#if defined(__CUDA_ARCH__) && !defined(TB_PORTABLE_FIELD)
+#define TB_PTX_FIELD 1
+// One row of the operand-scanning Montgomery product: t[0..8] += a[0..7] * bi.
+// The eight 32x32+32 -> 64-bit products are independent IMAD.WIDE.U32 (no carries); their high words are folded into
+// the next limb with a single add-with-carry chain.  (sm_100 has no IMAD with carry-out: `madc.lo.cc` costs an extra
+// IADD3.X per product, so the carries are kept off the multiplier.)  Requires t[8] == 0 on entry.
+__device__ __forceinline__ void tb_mul_row(uint32_t* t, const uint32_t* a, uint32_t bi) {
+  uint32_t lo[8], hi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint64_t p = (uint64_t)a[j] * bi + t[j];
+    lo[j] = (uint32_t)p; hi[j] = (uint32_t)(p >> 32);
+  }
+  t[0] = lo[0];
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, 0;"
+      : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8])
+      : "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]), "r"(hi[7]),
+        "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]));
+}
+// Pasta-specific reduction row: q = -t0 (since -m^-1 = -1 mod 2^32), t += q * m with m = 1 + m1 2^32 + m2 2^64 + m3 2^96 + 2^30 2^224;
+// afterwards t[0] == 0 and the caller shifts the window down by one limb.
+__device__ __forceinline__ void tb_red_row(uint32_t* t, uint32_t m1, uint32_t m2, uint32_t m3) {
+  const uint32_t q = 0u - t[0], ql = q << 30, qh = q >> 2;
+  const uint64_t r1 = (uint64_t)q * m1 + t[1], r2 = (uint64_t)q * m2 + t[2], r3 = (uint64_t)q * m3 + t[3];
+  asm("add.cc.u32 %0, %0, %9;\n\t"         // t0 + q = 0 (mod 2^32), carry = (t0 != 0)
+      "addc.cc.u32 %1, %10, 0;\n\t"
+      "addc.cc.u32 %2, %11, %13;\n\t"
+      "addc.cc.u32 %3, %12, %14;\n\t"
+      "addc.cc.u32 %4, %4, %15;\n\t"
+      "addc.cc.u32 %5, %5, 0;\n\t"
+      "addc.cc.u32 %6, %6, 0;\n\t"
+      "addc.cc.u32 %7, %7, %16;\n\t"
+      "addc.u32 %8, %8, %17;"
+      : "+r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
+      : "r"(q), "r"((uint32_t)r1), "r"((uint32_t)r2), "r"((uint32_t)r3), "r"((uint32_t)(r1 >> 32)), "r"((uint32_t)(r2 >> 32)), "r"((uint32_t)(r3 >> 32)),
+        "r"(ql), "r"(qh));
+}
+#endif
+
 template <class P>
 struct alignas(16) Fe {
   uint32_t l[8];
@@ -70,6 +117,23 @@ struct alignas(16) Fe {
 
   // r = a - m if a >= m (a < 2m)
   static TB_HD void cond_sub(uint32_t* a) {
+#ifdef TB_PTX_FIELD
+    uint32_t t[8], br;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, 0;\n\t"
+        "subc.cc.u32 %5, %14, 0;\n\t"
+        "subc.cc.u32 %6, %15, 0;\n\t"
+        "subc.cc.u32 %7, %16, %21;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(br)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(P::m(0)), "r"(P::m(1)), "r"(P::m(2)), "r"(P::m(3)), "r"(P::m(7)));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = br ? a[i] : t[i];
+    return;
+#else
     uint32_t t[8]; uint64_t br = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { uint64_t d = (uint64_t)a[i] - P::m(i) - br; t[i] = (uint32_t)d; br = (d >> 32) & 1; }
@@ -77,15 +141,60 @@ struct alignas(16) Fe {
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[i] = t[i];
     }
+#endif
   }
   friend TB_HD Fe operator+(const Fe& a, const Fe& b) {
+#ifdef TB_PTX_FIELD
+    Fe r;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+    cond_sub(r.l);
+    return r;
+#else
     Fe r; uint64_t c = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { c += (uint64_t)a.l[i] + b.l[i]; r.l[i] = (uint32_t)c; c >>= 32; }
     cond_sub(r.l);  // a+b < 2m < 2^256: no carry out
     return r;
+#endif
   }
   friend TB_HD Fe operator-(const Fe& a, const Fe& b) {
+#ifdef TB_PTX_FIELD
+    Fe r; uint32_t br;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]), "=r"(br)
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+    // br = 0xffffffff on borrow: add m back
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.u32 %7, %7, %12;"
+        : "+r"(r.l[0]), "+r"(r.l[1]), "+r"(r.l[2]), "+r"(r.l[3]), "+r"(r.l[4]), "+r"(r.l[5]), "+r"(r.l[6]), "+r"(r.l[7])
+        : "r"(br & P::m(0)), "r"(br & P::m(1)), "r"(br & P::m(2)), "r"(br & P::m(3)), "r"(br & P::m(7)));
+    return r;
+#else
     Fe r; uint64_t br = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { uint64_t d = (uint64_t)a.l[i] - b.l[i] - br; r.l[i] = (uint32_t)d; br = (d >> 32) & 1; }
@@ -93,12 +202,32 @@ struct alignas(16) Fe {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { c += (uint64_t)r.l[i] + (P::m(i) & mask); r.l[i] = (uint32_t)c; c >>= 32; }
     return r;
+#endif
   }
   TB_HD Fe neg() const { return zero() - *this; }
   TB_HD Fe dbl() const { return *this + *this; }
 
   // Montgomery product a*b*R^-1 mod m (CIOS, 32-bit limbs, Pasta-specific reduction row)
   friend TB_HD Fe operator*(const Fe& a, const Fe& b) {
+#ifdef TB_PTX_FIELD
+    // requires a < m (any 256-bit b): invariant t < 2m after every row, so 9 limbs never overflow
+    uint32_t t[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      tb_mul_row(t, a.l, b.l[i]);
+      tb_red_row(t, P::m(1), P::m(2), P::m(3));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = t[j + 1];
+      t[8] = 0;
+    }
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = t[i];
+    cond_sub(r.l);
+    return r;
+#else
     uint32_t t[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) t[i] = 0;
@@ -127,6 +256,7 @@ struct alignas(16) Fe {
     for (int i = 0; i < 8; ++i) r.l[i] = t[i];
     cond_sub(r.l);  // result < 2m, t8 == 0
     return r;
+#endif
   }
   TB_HD Fe sqr() const { return (*this) * (*this); }
 

@@ -135,6 +135,18 @@ __global__ void __launch_bounds__(256) msm_combine_kernel(const uint32_t* __rest
   if (lane == 0) buckets[b] = acc;
 }
 
+// same, one thread per bucket: cheaper when buckets have only a few units (large batches, chunk = 64)
+template <class B>
+__global__ void __launch_bounds__(128) msm_combine_serial_kernel(const uint32_t* __restrict__ unit_off, const Xyzz<B>* __restrict__ partial, uint32_t nb_total,
+                                                                  Xyzz<B>* __restrict__ buckets) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb_total) return;
+  uint32_t u0 = unit_off[b], u1 = unit_off[b + 1];
+  Xyzz<B> acc = Xyzz<B>::inf();
+  for (uint32_t u = u0; u < u1; ++u) acc.add(partial[u]);
+  buckets[b] = acc;
+}
+
 // running-sum reduction of one segment of `seg` buckets: sum_b (b+1) * bucket_b restricted to the segment
 template <class B>
 __global__ void __launch_bounds__(128) msm_segsum_kernel(const Xyzz<B>* __restrict__ buckets, int NB, int seg, int nt, uint32_t groups,
@@ -223,7 +235,10 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
                                                                           nb_total, 1u << chunk_log, entries.get(), partial.get());
   TB_LAUNCH_CHECK();
   ps.reset(); ps.reset(new ProfScope(ctx, PC_MSM_REDUCE));
-  msm_combine_kernel<B><<<(unsigned)(((uint64_t)nb_total * 32 + 255) / 256), 256, 0, st>>>(unit_off.get(), partial.get(), nb_total, buckets.get());
+  if ((max_entries >> chunk_log) <= 4 * nb_total64)  // few units per bucket on average: one thread per bucket
+    msm_combine_serial_kernel<B><<<(nb_total + 127) / 128, 128, 0, st>>>(unit_off.get(), partial.get(), nb_total, buckets.get());
+  else
+    msm_combine_kernel<B><<<(unsigned)(((uint64_t)nb_total * 32 + 255) / 256), 256, 0, st>>>(unit_off.get(), partial.get(), nb_total, buckets.get());
   TB_LAUNCH_CHECK();
 
   const int seg = NB < MSM_SEG ? NB : MSM_SEG;

@@ -62,7 +62,7 @@ __device__ Fp reduce_wide(const uint32_t* w) {
   Fp lo, hi;
   for (int i = 0; i < 8; ++i) { lo.l[i] = w[i]; hi.l[i] = w[8 + i]; }
   Fp r2 = Fp::r2();
-  return lo * r2 + (hi * r2) * r2;
+  return r2 * lo + r2 * (r2 * hi);  // the reduced operand goes first: Fe::operator* needs a < m, b may be any 256-bit value
 }
 
 __device__ Fp tr_squeeze_one(TrState& s) {

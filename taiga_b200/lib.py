@@ -233,16 +233,18 @@ class ProvingKey:
         assert adv.size % per == 0
         return self.prove_batch_raw(adv, adv.size // per, instance, instance_len, seed, first_proof_index)
 
-    def prove_batch_raw(self, advice, B, instance, instance_len, seed, first_proof_index=0):
-        """Same, with `advice` given as anything exposing its address (numpy array, pinned-host or DEVICE torch tensor)."""
+    def prove_batch_raw(self, advice, B, instance, instance_len, seed, first_proof_index=0, ctx=None):
+        """Same, with `advice` given as anything exposing its address (numpy array, pinned-host or DEVICE torch tensor).
+        `ctx`: run on another Context (= another CUDA stream) of the same device, e.g. to overlap two circuits."""
+        ctx = ctx or self.ctx
         inst = _u8(instance)
         lens = np.ascontiguousarray(instance_len, dtype=np.uint32)
         assert inst.size >= B * int(lens.sum()) * 32
         seed = _u8(np.frombuffer(bytes(seed), np.uint8))
         assert seed.size == 32
         out = np.zeros((B, self.proof_len), np.uint8)
-        self.ctx._check(self.ctx._lib.tb_prove_batch(self.ctx._h, self._h, B, _ptr(advice), _ptr(inst), _ptr(lens), _ptr(seed), first_proof_index,
-                                                     _ptr(out), self.proof_len))
+        ctx._check(ctx._lib.tb_prove_batch(ctx._h, self._h, B, _ptr(advice), _ptr(inst), _ptr(lens), _ptr(seed), first_proof_index,
+                                           _ptr(out), self.proof_len))
         return [out[b].tobytes() for b in range(B)]
 
     def close(self):

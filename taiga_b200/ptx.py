@@ -14,6 +14,8 @@ The circuits are the Taiga-shaped ones of circuits_taiga.py (the real ones need 
 synthesis happens on the host before the call, exactly as `Circuit::synthesize` does in the reference; it is not part
 of the proving hot path and not part of any timed region.
 """
+import threading
+
 import numpy as np
 
 from . import circuits_taiga, lib
@@ -42,6 +44,7 @@ class ProverService:
 
     def __init__(self, device=0, srs_arrays=None):
         self.ctx = lib.Context(device)
+        self.ctx2 = lib.Context(device)   # second stream: the VP batch overlaps the Compliance batch
         s = srs_arrays
         self.srs = self.ctx.load_srs(s["k"], s["g"], s["g_lagrange"], s["w"], s["u"])
         self.kd_c, self.make_c = circuits_taiga.build(True)
@@ -63,12 +66,27 @@ class ProverService:
         c_adv / v_adv may override the advice buffers (e.g. pinned host or device-resident torch tensors)."""
         c_adv = wit["c_adv"] if c_adv is None else c_adv
         v_adv = wit["v_adv"] if v_adv is None else v_adv
-        cp = self._prove_chunks(self.pk_c, c_adv, wit["c_inst"], wit["c_len"], seed, max_batch, 0)
-        vp = self._prove_chunks(self.pk_v, v_adv, wit["v_inst"], wit["v_len"], seed, max_batch, 1 << 20)
-        return cp, vp
+        res = {}
+
+        def run_vp():
+            try:
+                res["vp"] = self._prove_chunks(self.pk_v, v_adv, wit["v_inst"], wit["v_len"], seed, max_batch, 1 << 20, self.ctx2)
+            except BaseException as ex:  # re-raised in the caller's thread
+                res["err"] = ex
+        th = threading.Thread(target=run_vp)
+        th.start()   # ctypes releases the GIL inside tb_prove_batch, so both batches are enqueued concurrently on two streams
+        cp = self._prove_chunks(self.pk_c, c_adv, wit["c_inst"], wit["c_len"], seed, max_batch, 0, self.ctx)
+        th.join()
+        if "err" in res:
+            raise res["err"]
+        return cp, res["vp"]
+
+    @property
+    def launch_count(self):
+        return self.ctx.launch_count + self.ctx2.launch_count
 
     @staticmethod
-    def _prove_chunks(pk, adv, inst, lens, seed, max_batch, index0):
+    def _prove_chunks(pk, adv, inst, lens, seed, max_batch, index0, ctx):
         kd = pk.keydata
         per = kd.cs.num_advice * kd.n * 32
         if hasattr(adv, "data_ptr"):  # torch tensor (pinned host or device)
@@ -82,7 +100,7 @@ class ProverService:
                 chunk = _TensorSlice(adv, s * per, (e - s) * per)
             else:
                 chunk = adv.reshape(total, -1)[s:e]
-            out += pk.prove_batch_raw(chunk, e - s, inst[s:e], lens, seed, index0 + s)
+            out += pk.prove_batch_raw(chunk, e - s, inst[s:e], lens, seed, index0 + s, ctx=ctx)
         return out
 
 
