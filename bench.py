@@ -212,7 +212,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from taiga_b200 import ptx
+    from taiga_b200 import ptx, shard
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -231,10 +231,9 @@ def main():
     def step(i, device_resident):
         seed = bytes((b + i) & 0xFF for b in seed0)
         proofs = svc.build_ptx_batch(wit, seed, c_dev if device_resident else c_pin, v_dev if device_resident else v_pin)
-        if world > 1:  # the only collective on the path: gather the finished proof bytes (fixed-size records)
-            rec = torch.from_numpy(np.frombuffer(b"".join(proofs[0] + proofs[1]), np.uint8).copy()).cuda()
-            bufs = [torch.empty_like(rec) for _ in range(world)]
-            dist.all_gather(bufs, rec)
+        if world > 1:  # the only collective on the path: gather the finished proof bytes (fixed-size records) over NCCL
+            rec = shard.pack_records(proofs[0], proofs[1], svc.pk_c.proof_len, svc.pk_v.proof_len)
+            shard.gather_records(rec, P * world, device="cuda")
         return proofs
 
     def timed(device_resident):
