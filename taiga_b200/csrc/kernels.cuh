@@ -13,7 +13,8 @@ template <class F> struct NttHook { int use_zeta; F z1, z2; uint32_t k; int mod_
 
 template <class F>
 void ntt_run(Ctx* ctx, int logn, bool inverse, const F* in, F* out, F* scratch, int batch, long long in_bstride,
-             long long out_bstride, const NttHook<F>* pre, const NttHook<F>* post);
+             long long out_bstride, const NttHook<F>* pre, const NttHook<F>* post, int batch2 = 1, long long in_b2stride = 0,
+             long long out_b2stride = 0);  // scratch must hold batch2 * batch * 2^logn elements
 template <class F> void build_twiddles(Ctx* ctx);
 template <class F> void free_twiddles(Ctx* ctx);
 
@@ -24,6 +25,7 @@ struct MsmConfig {
   int table_stride = 0;   // points per table window (>= N + n_extra); 0 = N
   int n_extra = 0;        // extra terms per MSM: scalar extra_scalars[k*n_extra + j] (Montgomery) times table point N + j
   const void* extra_scalars = nullptr;
+  void* affine_out = nullptr;  // fixed-base mode: also write the K results normalised to affine (Aff<B>[K])
 };
 int msm_default_window(int n, bool fixed_tables);
 // K multi-scalar multiplications of N terms.  scalars: Montgomery form, item k at scalars + k*scalar_bstride.

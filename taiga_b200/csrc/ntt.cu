@@ -25,7 +25,8 @@ struct NttArgs {
   int logn, r, sh, last, npass, pass;
   int rs[3];
   int logT;
-  long long in_bstride, out_bstride;  // elements between batch items
+  long long in_bstride, out_bstride;  // elements between batch items (blockIdx.y)
+  long long in_b2stride, out_b2stride;  // second batch dimension (blockIdx.z), e.g. proofs
   NttHook<F> pre, post;
 };
 
@@ -47,8 +48,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const F* __restri
   const int stride = (T == 1) ? 1 : T + 1;
   uint4* slo = smem;
   uint4* shi = smem + R * stride;
-  in += (long long)blockIdx.y * a.in_bstride;
-  out += (long long)blockIdx.y * a.out_bstride;
+  in += (long long)blockIdx.y * a.in_bstride + (long long)blockIdx.z * a.in_b2stride;
+  out += (long long)blockIdx.y * a.out_bstride + (long long)blockIdx.z * a.out_b2stride;
   const uint32_t lane0 = blockIdx.x << a.logT;
   const int logn = a.logn;
 
@@ -124,9 +125,9 @@ static void ntt_plan(int logn, int* rs, int* npass) {
 
 template <class F>
 void ntt_run(Ctx* ctx, int logn, bool inverse, const F* in, F* out, F* scratch, int batch, long long in_bstride,
-             long long out_bstride, const NttHook<F>* pre, const NttHook<F>* post) {
+             long long out_bstride, const NttHook<F>* pre, const NttHook<F>* post, int batch2, long long in_b2stride, long long out_b2stride) {
   TB_REQUIRE(logn >= 1 && logn <= TW_LOG, "NTT size out of range");
-  TB_REQUIRE(batch >= 1 && batch <= 65535, "NTT batch out of range");
+  TB_REQUIRE(batch >= 1 && batch <= 65535 && batch2 >= 1 && batch2 <= 65535, "NTT batch out of range");
   ProfScope prof_scope(ctx, PC_NTT);
   static bool attr_set[2] = {false, false};
   if (!attr_set[F::params_id()]) {
@@ -155,17 +156,19 @@ void ntt_run(Ctx* ctx, int logn, bool inverse, const F* in, F* out, F* scratch, 
     F* dst = a.last ? out : scratch;
     a.in_bstride = (p == 0) ? in_bstride : (long long)(1ll << logn);
     a.out_bstride = a.last ? out_bstride : (long long)(1ll << logn);
+    a.in_b2stride = (p == 0) ? in_b2stride : (long long)batch * (1ll << logn);   // scratch is [batch2][batch][N]
+    a.out_b2stride = a.last ? out_b2stride : (long long)batch * (1ll << logn);
     int R = 1 << a.r, T = 1 << a.logT;
     size_t smem = (size_t)R * (T == 1 ? 1 : T + 1) * 32;
-    dim3 grid((1u << lanes_log) >> a.logT, batch);
+    dim3 grid((1u << lanes_log) >> a.logT, batch, batch2);
     ntt_pass_kernel<F><<<grid, NTT_THREADS, smem, ctx->stream>>>(src, dst, a);
     TB_LAUNCH_CHECK();
     ctx->launches++;
   }
 }
 
-template void ntt_run<Fp>(Ctx*, int, bool, const Fp*, Fp*, Fp*, int, long long, long long, const NttHook<Fp>*, const NttHook<Fp>*);
-template void ntt_run<Fq>(Ctx*, int, bool, const Fq*, Fq*, Fq*, int, long long, long long, const NttHook<Fq>*, const NttHook<Fq>*);
+template void ntt_run<Fp>(Ctx*, int, bool, const Fp*, Fp*, Fp*, int, long long, long long, const NttHook<Fp>*, const NttHook<Fp>*, int, long long, long long);
+template void ntt_run<Fq>(Ctx*, int, bool, const Fq*, Fq*, Fq*, int, long long, long long, const NttHook<Fq>*, const NttHook<Fq>*, int, long long, long long);
 
 // ---- twiddle table construction (host arithmetic with the same field code, uploaded once per context)
 template <class F>

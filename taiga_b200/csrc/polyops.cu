@@ -261,6 +261,7 @@ __global__ void scalar_program_kernel(Fp* vars, long long stride, const ScalarIn
       case S_CONST: r = consts[in.imm]; break;
       case S_NEG: r = v[in.a].neg(); break;
       case S_FMA: r = v[in.dst] * v[in.a] + v[in.b]; break;
+      case S_POWI: r = v[in.a].pow_u64((uint64_t)in.imm); break;
       default: r = Fp::zero();
     }
     v[in.dst] = r;

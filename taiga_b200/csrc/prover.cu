@@ -34,6 +34,7 @@ struct Circuit {
   Fp *l0 = nullptr, *l_last = nullptr, *l_blind = nullptr, *consts = nullptr, *wr_inv = nullptr;
   int2 *d_aq = nullptr, *d_fq = nullptr, *d_iq = nullptr, *d_perm = nullptr;
   QProgram prog_gates, prog_lookups;
+  std::map<int, std::vector<QProgram>> gate_parts; std::map<int, std::vector<int>> gate_part_counts;   // keyed by number of parts
   std::vector<Fp> t_inv; Fp delta, zeta, omega, r_inv;
   Fp delta_c0[16];
   // evaluation / multiopen structure (host)
@@ -52,6 +53,7 @@ struct Circuit {
     for (void* p : {(void*)fixed_vals, (void*)fixed_polys, (void*)fixed_cosets, (void*)sig_vals, (void*)sig_polys, (void*)sig_cosets, (void*)l0, (void*)l_last,
                     (void*)l_blind, (void*)consts, (void*)wr_inv, (void*)d_aq, (void*)d_fq, (void*)d_iq, (void*)d_perm, (void*)prog_gates.dev, (void*)prog_lookups.dev})
       if (p) cudaFree(p);
+    for (auto& kv : gate_parts) for (auto& qp : kv.second) if (qp.dev) cudaFree(qp.dev);
   }
 };
 
@@ -156,6 +158,7 @@ static Circuit* circuit_load(Ctx* ctx, const Srs* srs, const tb_cs_desc* cs, con
   // expression programs (descriptor rebuilt from the deep copy so pointers stay valid)
   { tb_cs_desc d = *cs;
     q_compile_gates(&d, &C.prog_gates);
+    for (int parts : {1, 2, 4, 8}) q_compile_gates_split(&d, parts, &C.gate_parts[parts], &C.gate_part_counts[parts]);
     q_compile_lookups(&d, &C.prog_lookups); }
 
   // ---- evaluation section order (plonk/prover.rs) and multiopen query order
@@ -278,6 +281,11 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   const Srs& srs = *C.srs;
   const size_t n = C.n; const long long nn = (long long)n; const int k = (int)C.k; const int na = C.na, ni = C.ni, L = C.L, nsets = C.nsets, P = C.P, bf = C.bf;
   const int ni1 = std::max(1, ni), L1 = std::max(1, L), ns1 = std::max(1, nsets);
+  // all per-proof polynomials that are taken to the extended cosets live in ONE buffer [B][NC][n] so that each sub-coset
+  // needs a single batched NTT launch: advice | instance | permutation Z | lookup Z | A' | S'
+  const int NC = na + ni + nsets + 3 * L;
+  const int O_ADV = 0, O_INST = na, O_PZ = na + ni, O_LZ = na + ni + nsets, O_LPIN = O_LZ + L, O_LPTAB = O_LZ + 2 * L;
+  const long long PS = (long long)NC * nn;   // per-proof stride of the merged buffers
   cudaStream_t st = ctx->stream;
   size_t inst_total = 0;
   for (int c = 0; c < ni; ++c) { TB_REQUIRE(instance_len[c] <= C.usable, "InstanceTooLarge"); inst_total += instance_len[c]; }
@@ -305,6 +313,7 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   const int V_QBLIND = va.one(nps), V_P_BLIND = va.one(), V_S_BLIND = va.one(), V_F = va.one();
   const int V_S_AT = va.one(), V_V = va.one(), V_LR = va.one(), V_RR = va.one(), V_VL = va.one(), V_VR = va.one();
   const int V_U = va.one(), V_UINV = va.one(), V_T0 = va.one(), V_C = va.one();
+  const int V_YPOW = va.one(Q_MAX_PARTS);
   const int NV = va.next;
   WBuf<Fp> vars = ws.buf<Fp>((size_t)B * NV);
   vars.zero();
@@ -320,13 +329,15 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   auto VP = [&](int slot) { return vars.get() + slot; };  // pointer to slot of proof 0, stride NV
 
   Transcripts tr; tr.init(ctx, B, C.proof_len, C.vk_repr);
-  WBuf<Fp> scratch = ws.buf<Fp>((size_t)B * std::max({na, ni1, L1 * 3, ns1, (int)C.pieces, 4}) * n);
+  WBuf<Fp> scratch = ws.buf<Fp>((size_t)B * std::max({NC, (int)C.pieces, 4}) * n);
+  WBuf<Fp> polys = ws.buf<Fp>((size_t)B * NC * n), cosets = ws.buf<Fp>((size_t)B * NC * n);
   WBuf<Aff<Fq>> pts = ws.buf<Aff<Fq>>((size_t)B * std::max({na, ni1, 2 * L1, ns1, (int)C.pieces, 2}));
   WBuf<Fp> blinds = ws.buf<Fp>((size_t)B * std::max({na, ni1, L1, ns1, (int)C.pieces, 4}));
   WBuf<uint32_t> derr = ws.buf<uint32_t>(1); derr.zero();
 
   // ---- instance columns: pad, commit_lagrange(Blind::default() = 1) -> common_point, iNTT
-  WBuf<Fp> inst_vals = ws.buf<Fp>((size_t)B * ni1 * n), inst_polys = ws.buf<Fp>((size_t)B * ni1 * n);
+  WBuf<Fp> inst_vals = ws.buf<Fp>((size_t)B * ni1 * n);
+  Fp* const inst_polys = polys.get() + (size_t)O_INST * n;
   inst_vals.zero();
   if (ni) {
     size_t off = 0;
@@ -340,10 +351,11 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
     fill_const_kernel<<<(B * ni + 63) / 64, 64, 0, st>>>(blinds.get(), (size_t)B * ni, Fp::one());
     srs.commit(ctx, true, inst_vals.get(), nn, B * ni, blinds.get(), pts.get());
     tr.points(pts.get(), ni, ni, false);
-    ntt_run<Fp>(ctx, k, true, inst_vals.get(), inst_polys.get(), scratch.get(), B * ni, nn, nn, nullptr, nullptr);
+    ntt_run<Fp>(ctx, k, true, inst_vals.get(), inst_polys, scratch.get(), ni, nn, nn, nullptr, nullptr, B, (long long)ni * nn, PS);
   }
   // ---- advice columns: upload, blinding rows, commit, iNTT
-  WBuf<Fp> adv_vals = ws.buf<Fp>((size_t)B * na * n), adv_polys = ws.buf<Fp>((size_t)B * na * n);
+  WBuf<Fp> adv_vals = ws.buf<Fp>((size_t)B * na * n);
+  Fp* const adv_polys = polys.get() + (size_t)O_ADV * n;
   TB_CUDA(cudaMemcpyAsync(adv_vals.get(), advice_host, (size_t)B * na * n * 32, cudaMemcpyDefault, st));  // host or device pointer
   fe_to_mont<Fp>(ctx, adv_vals.get(), (size_t)B * na * n);
   for (int c = 0; c < na; ++c)
@@ -352,12 +364,12 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   poly_copy(ctx, blinds.get(), na, VP(V_ADV_BLIND), NV, na, B);
   srs.commit(ctx, true, adv_vals.get(), nn, B * na, blinds.get(), pts.get());
   tr.points(pts.get(), na, na, true);
-  ntt_run<Fp>(ctx, k, true, adv_vals.get(), adv_polys.get(), scratch.get(), B * na, nn, nn, nullptr, nullptr);
+  ntt_run<Fp>(ctx, k, true, adv_vals.get(), adv_polys, scratch.get(), na, nn, nn, nullptr, nullptr, B, (long long)na * nn, PS);
   tr.squeeze(VP(V_THETA), NV, 1);
 
   // ---- lookups: compress (Lagrange domain), sort, arrange, blind, commit A', S'
   WBuf<Fp> lkA = ws.buf<Fp>((size_t)B * L1 * n), lkS = ws.buf<Fp>((size_t)B * L1 * n), lpin = ws.buf<Fp>((size_t)B * L1 * n), lptab = ws.buf<Fp>((size_t)B * L1 * n);
-  WBuf<Fp> lpin_polys = ws.buf<Fp>((size_t)B * L1 * n), lptab_polys = ws.buf<Fp>((size_t)B * L1 * n);
+  Fp* const lpin_polys = polys.get() + (size_t)O_LPIN * n; Fp* const lptab_polys = polys.get() + (size_t)O_LPTAB * n;
   QData qd; memset(&qd, 0, sizeof(qd));
   qd.aq = C.d_aq; qd.fq = C.d_fq; qd.iq = C.d_iq; qd.consts = C.consts; qd.chal = vars.get(); qd.chal_stride = NV; qd.y_slot = V_Y; qd.theta_slot = V_THETA;
   qd.n = (int)n; qd.lk_pstride = (long long)L1 * nn;
@@ -387,14 +399,14 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
     poly_copy(ctx, blinds.get(), L, VP(V_LPTAB_BLIND), NV, L, B);
     srs.commit(ctx, true, lptab.get(), nn, B * L, blinds.get(), ps.get());
     for (int l = 0; l < L; ++l) { tr.points(pa.get() + l, L, 1, true); tr.points(ps.get() + l, L, 1, true); }
-    ntt_run<Fp>(ctx, k, true, lpin.get(), lpin_polys.get(), scratch.get(), B * L, nn, nn, nullptr, nullptr);
-    ntt_run<Fp>(ctx, k, true, lptab.get(), lptab_polys.get(), scratch.get(), B * L, nn, nn, nullptr, nullptr);
+    ntt_run<Fp>(ctx, k, true, lpin.get(), lpin_polys, scratch.get(), L, nn, nn, nullptr, nullptr, B, (long long)L * nn, PS);
+    ntt_run<Fp>(ctx, k, true, lptab.get(), lptab_polys, scratch.get(), L, nn, nn, nullptr, nullptr, B, (long long)L * nn, PS);
   }
   tr.squeeze(VP(V_BETA), NV, 1);
   tr.squeeze(VP(V_GAMMA), NV, 1);
 
   // ---- permutation grand products
-  WBuf<Fp> pz_polys = ws.buf<Fp>((size_t)B * ns1 * n);
+  Fp* const pz_polys = polys.get() + (size_t)O_PZ * n;
   const size_t gp = (size_t)std::max(ns1, L1);
   WBuf<Fp> gnum = ws.buf<Fp>((size_t)B * gp * n), gden = ws.buf<Fp>((size_t)B * gp * n), gz = ws.buf<Fp>((size_t)B * gp * n);
   if (nsets) {
@@ -414,10 +426,10 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
     poly_copy(ctx, blinds.get(), nsets, VP(V_PZ_BLIND), NV, nsets, B);
     srs.commit(ctx, true, gz.get(), nn, B * nsets, blinds.get(), pts.get());
     tr.points(pts.get(), nsets, nsets, true);
-    ntt_run<Fp>(ctx, k, true, gz.get(), pz_polys.get(), scratch.get(), B * nsets, nn, nn, nullptr, nullptr);
+    ntt_run<Fp>(ctx, k, true, gz.get(), pz_polys, scratch.get(), nsets, nn, nn, nullptr, nullptr, B, (long long)nsets * nn, PS);
   }
   // ---- lookup grand products
-  WBuf<Fp> lz_polys = ws.buf<Fp>((size_t)B * L1 * n);
+  Fp* const lz_polys = polys.get() + (size_t)O_LZ * n;
   if (L) {
     lookup_fractions(ctx, lkA.get(), lkS.get(), lpin.get(), lptab.get(), gnum.get(), gden.get(), (long long)L * nn, L, (int)n, vars.get(), NV, V_BETA, V_GAMMA, B);
     batch_inverse(ctx, gden.get(), (size_t)B * L * n);
@@ -429,7 +441,7 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
     poly_copy(ctx, blinds.get(), L, VP(V_LZ_BLIND), NV, L, B);
     srs.commit(ctx, true, gz.get(), nn, B * L, blinds.get(), pts.get());
     tr.points(pts.get(), L, L, true);
-    ntt_run<Fp>(ctx, k, true, gz.get(), lz_polys.get(), scratch.get(), B * L, nn, nn, nullptr, nullptr);
+    ntt_run<Fp>(ctx, k, true, gz.get(), lz_polys, scratch.get(), L, nn, nn, nullptr, nullptr, B, (long long)L * nn, PS);
   }
   // ---- vanishing argument: random polynomial
   WBuf<Fp> random_poly = ws.buf<Fp>((size_t)B * n);
@@ -442,29 +454,26 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
 
   // ---- quotient, tiled by sub-coset
   const int R = C.R;
+  int gparts = 1;   // constraint-parallel split of the gate program when the batch alone cannot fill the GPU
+  { long long ctas = (long long)B * ((nn + 127) / 128); while (gparts < Q_MAX_PARTS && ctas * gparts < 4LL * ctx->sm_count) gparts *= 2; }
+  const std::vector<QProgram>& gprogs = C.gate_parts.at(gparts); const std::vector<int>& gcounts = C.gate_part_counts.at(gparts);
+  { Prog p; for (size_t i = 1; i < gprogs.size(); ++i) p.op(S_POWI, V_YPOW + (int)i, V_Y, 0, (uint32_t)gcounts[i]); run_prog(p); }
   WBuf<Fp> hext = ws.buf<Fp>((size_t)B * R * n), hcoef = ws.buf<Fp>((size_t)B * C.pieces * n);
-  { WBuf<Fp> c_adv = ws.buf<Fp>((size_t)B * na * n), c_inst = ws.buf<Fp>((size_t)B * ni1 * n), c_pz = ws.buf<Fp>((size_t)B * ns1 * n), c_lz = ws.buf<Fp>((size_t)B * L1 * n),
-        c_lpin = ws.buf<Fp>((size_t)B * L1 * n), c_lptab = ws.buf<Fp>((size_t)B * L1 * n), c_lkA = ws.buf<Fp>((size_t)B * L1 * n), c_lkS = ws.buf<Fp>((size_t)B * L1 * n),
-        gate = ws.buf<Fp>((size_t)B * n), V = ws.buf<Fp>((size_t)B * R * n);
+  { WBuf<Fp> c_lkA = ws.buf<Fp>((size_t)B * L1 * n), c_lkS = ws.buf<Fp>((size_t)B * L1 * n), gate = ws.buf<Fp>((size_t)Q_MAX_PARTS * B * n), V = ws.buf<Fp>((size_t)B * R * n);
+    Fp* const c_adv = cosets.get() + (size_t)O_ADV * n; Fp* const c_inst = cosets.get() + (size_t)O_INST * n; Fp* const c_pz = cosets.get() + (size_t)O_PZ * n;
+    Fp* const c_lz = cosets.get() + (size_t)O_LZ * n; Fp* const c_lpin = cosets.get() + (size_t)O_LPIN * n; Fp* const c_lptab = cosets.get() + (size_t)O_LPTAB * n;
     for (int k1 = 0; k1 < R; ++k1) {
       NttHook<Fp> h = coset_hook(C, k1, false);
-      ntt_run<Fp>(ctx, k, false, adv_polys.get(), c_adv.get(), scratch.get(), B * na, nn, nn, &h, nullptr);
-      if (ni) ntt_run<Fp>(ctx, k, false, inst_polys.get(), c_inst.get(), scratch.get(), B * ni, nn, nn, &h, nullptr);
-      if (nsets) ntt_run<Fp>(ctx, k, false, pz_polys.get(), c_pz.get(), scratch.get(), B * nsets, nn, nn, &h, nullptr);
-      if (L) {
-        ntt_run<Fp>(ctx, k, false, lz_polys.get(), c_lz.get(), scratch.get(), B * L, nn, nn, &h, nullptr);
-        ntt_run<Fp>(ctx, k, false, lpin_polys.get(), c_lpin.get(), scratch.get(), B * L, nn, nn, &h, nullptr);
-        ntt_run<Fp>(ctx, k, false, lptab_polys.get(), c_lptab.get(), scratch.get(), B * L, nn, nn, &h, nullptr);
-      }
-      qd.adv = c_adv.get(); qd.adv_pstride = (long long)na * nn; qd.inst = c_inst.get(); qd.inst_pstride = (long long)ni1 * nn;
+      ntt_run<Fp>(ctx, k, false, polys.get(), cosets.get(), scratch.get(), B * NC, nn, nn, &h, nullptr);
+      qd.adv = c_adv; qd.adv_pstride = PS; qd.inst = c_inst; qd.inst_pstride = PS;
       qd.fix = C.fixed_cosets; qd.R = R; qd.k1 = k1; qd.lkA = c_lkA.get(); qd.lkS = c_lkS.get();
       qd.gate_out = gate.get(); qd.gate_pstride = nn;
-      q_run(ctx, C.prog_gates, qd, B);
+      q_run_parts(ctx, gprogs, qd, (long long)B * nn, B);
       if (L) { qd.gate_out = nullptr; q_run(ctx, C.prog_lookups, qd, B); }
       QFinish f; memset(&f, 0, sizeof(f));
-      f.gate = gate.get(); f.adv = c_adv.get(); f.adv_pstride = (long long)na * nn; f.inst = c_inst.get(); f.inst_pstride = (long long)ni1 * nn;
+      f.gate = gate.get(); f.nparts = (int)gprogs.size(); f.gate_part_stride = (long long)B * nn; f.ypow_slot = V_YPOW; f.adv = c_adv; f.adv_pstride = PS; f.inst = c_inst; f.inst_pstride = PS;
       f.fix = C.fixed_cosets; f.sig = C.sig_cosets; f.R = R; f.k1 = k1; f.l0 = C.l0; f.l_last = C.l_last; f.l_blind = C.l_blind;
-      f.pz = c_pz.get(); f.pz_pstride = (long long)ns1 * nn; f.lz = c_lz.get(); f.lpin = c_lpin.get(); f.lptab = c_lptab.get(); f.lk_pstride = (long long)L1 * nn;
+      f.pz = c_pz; f.pz_pstride = PS; f.lz = c_lz; f.lpin = c_lpin; f.lptab = c_lptab; f.lk_pstride = PS; f.lkc_pstride = (long long)L1 * nn;
       f.lkA = c_lkA.get(); f.lkS = c_lkS.get(); f.perm_cols = C.d_perm; f.P = P; f.chunk = C.chunk; f.nsets = nsets; f.L = L; f.bf = bf;
       f.chal = vars.get(); f.chal_stride = NV; f.y_slot = V_Y; f.beta_slot = V_BETA; f.gamma_slot = V_GAMMA;
       f.delta = C.delta; f.zeta = C.zeta; f.t_inv = C.t_inv[k1]; memcpy(f.delta_c0, C.delta_c0, sizeof(f.delta_c0)); f.tw = ctx->tw_fp.fwd;
@@ -504,12 +513,12 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   struct PRef { const Fp* base; long long bstride; int blind_slot; };
   auto poly_ref = [&](const PolyId& id) -> PRef {
     switch (id.kind) {
-      case PK_INST: return {inst_polys.get() + (size_t)id.idx * n, (long long)ni1 * nn, V_ONE};
-      case PK_ADV: return {adv_polys.get() + (size_t)id.idx * n, (long long)na * nn, V_ADV_BLIND + id.idx};
-      case PK_PZ: return {pz_polys.get() + (size_t)id.idx * n, (long long)ns1 * nn, V_PZ_BLIND + id.idx};
-      case PK_LZ: return {lz_polys.get() + (size_t)id.idx * n, (long long)L1 * nn, V_LZ_BLIND + id.idx};
-      case PK_LPIN: return {lpin_polys.get() + (size_t)id.idx * n, (long long)L1 * nn, V_LPIN_BLIND + id.idx};
-      case PK_LPTAB: return {lptab_polys.get() + (size_t)id.idx * n, (long long)L1 * nn, V_LPTAB_BLIND + id.idx};
+      case PK_INST: return {inst_polys + (size_t)id.idx * n, PS, V_ONE};
+      case PK_ADV: return {adv_polys + (size_t)id.idx * n, PS, V_ADV_BLIND + id.idx};
+      case PK_PZ: return {pz_polys + (size_t)id.idx * n, PS, V_PZ_BLIND + id.idx};
+      case PK_LZ: return {lz_polys + (size_t)id.idx * n, PS, V_LZ_BLIND + id.idx};
+      case PK_LPIN: return {lpin_polys + (size_t)id.idx * n, PS, V_LPIN_BLIND + id.idx};
+      case PK_LPTAB: return {lptab_polys + (size_t)id.idx * n, PS, V_LPTAB_BLIND + id.idx};
       case PK_FIXED: return {C.fixed_polys + (size_t)id.idx * n, 0, V_ONE};
       case PK_SIG: return {C.sig_polys + (size_t)id.idx * n, 0, V_ONE};
       case PK_H: return {h_poly.get(), nn, V_H_BLIND};
@@ -605,8 +614,8 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
     prf_fill(ctx, seed, proof0, R_IPA_R, (uint32_t)j, VP(V_RR), NV, 1, 1, B);
     ipa_extras_kernel<<<(B + 31) / 32, 32, 0, st>>>(ex.get(), vars.get(), NV, V_LR, V_RR, V_VL, V_VR, V_Z, B);
     // L_j, R_j = <cL | cR, g> + l_rand * w + (value * z) * u : one batched fixed-base MSM, K = 2 per proof
-    srs.commit_xyzz(ctx, false, cLR.get(), nn, 2 * B, ex.get(), 2, accLR.get());
-    points_to_affine<Fq>(ctx, accLR.get(), 2 * B, ptLR.get());
+    srs.commit_xyzz(ctx, false, cLR.get(), nn, 2 * B, ex.get(), 2, accLR.get(), ptLR.get());
+    if (((1 << (srs.c - 1)) / 8) > 256) points_to_affine<Fq>(ctx, accLR.get(), 2 * B, ptLR.get());
     tr.points(ptLR.get(), 2, 2, true);
     tr.squeeze(VP(V_U), NV, 1);
     scalar_program(ctx, vars.get(), NV, d_round, (int)round_prog.ins.size(), dconsts, B);

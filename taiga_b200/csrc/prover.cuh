@@ -52,7 +52,7 @@ void powers(Ctx* c, Fp* out, long long out_stride, const Fp* x, long long x_stri
 
 // ---------------------------------------------------------------- generic small per-proof scalar programs (prover.cu)
 // One thread per proof runs a tiny field program over a per-proof scratch vector (challenges, blinds, evaluation points).
-enum ScalarOp { S_MUL = 0, S_ADD, S_SUB, S_INV, S_COPY, S_POW2K /* dst = a^(2^imm) */, S_CONST /* dst = consts[imm] */, S_NEG, S_FMA /* dst = dst*a + b */ };
+enum ScalarOp { S_MUL = 0, S_ADD, S_SUB, S_INV, S_COPY, S_POW2K /* dst = a^(2^imm) */, S_CONST /* dst = consts[imm] */, S_NEG, S_FMA /* dst = dst*a + b */, S_POWI /* dst = a^imm */ };
 struct ScalarInstr { uint16_t op, dst, a, b; uint32_t imm; };
 void scalar_program(Ctx* c, Fp* vars, long long stride, const ScalarInstr* d_prog, int ninstr, const Fp* d_consts, int B);
 

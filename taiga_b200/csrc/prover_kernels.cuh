@@ -24,6 +24,11 @@ struct QProgram {           // compiled once per circuit (host), resident on the
 // Flattens the expression DAG reachable from `roots` into a register-allocated instruction list.
 // mode 0: gate constraints folded with y (Q_FOLD_Y per root);  mode 1: lookup compression (theta folds + stores)
 void q_compile_gates(const tb_cs_desc* cs, QProgram* out);
+// the constraint list split into `parts` contiguous groups of similar cost, one program each (row-parallel AND
+// constraint-parallel evaluation for small batches); counts[p] = number of constraints folded by part p
+constexpr int Q_MAX_PARTS = 8;
+void q_compile_gates_split(const tb_cs_desc* cs, int parts, std::vector<QProgram>* out, std::vector<int>* counts);
+struct QPartList { const QInstr* prog[Q_MAX_PARTS]; int ninstr[Q_MAX_PARTS]; int nparts; long long part_stride; };
 void q_compile_lookups(const tb_cs_desc* cs, QProgram* out);
 
 struct QData {
@@ -38,15 +43,18 @@ struct QData {
   int n;
 };
 void q_run(Ctx* c, const QProgram& prog, const QData& d, int B);
+void q_run_parts(Ctx* c, const std::vector<QProgram>& progs, QData d, long long part_stride, int B);
 
 // permutation + lookup terms of the quotient, folded onto the gate accumulator, times 1/(X^n - 1) (constant per sub-coset)
 struct QFinish {
-  const Fp* gate;          // [B][n]
+  const Fp* gate;          // [nparts][B][n] partial Horner sums of the gate constraints
+  int nparts; long long gate_part_stride; int ypow_slot;   // vars[ypow_slot + p] = y^(constraints in part p), p >= 1
   const Fp* adv; long long adv_pstride; const Fp* inst; long long inst_pstride;   // sub-coset evaluations
   const Fp* fix; const Fp* sig; int R; int k1;      // [nf][R][n], [P][R][n]
   const Fp* l0; const Fp* l_last; const Fp* l_blind; // [R][n]
   const Fp* pz; long long pz_pstride;                // [B][nsets][n]
-  const Fp* lz; const Fp* lpin; const Fp* lptab; long long lk_pstride;  // [B][L][n] each
+  const Fp* lz; const Fp* lpin; const Fp* lptab; long long lk_pstride;  // per-proof stride of the three (merged coset buffer)
+  long long lkc_pstride;                             // per-proof stride of lkA / lkS
   const Fp* lkA; const Fp* lkS;                      // [B][L][n] compressed input / table on this sub-coset
   const int2* perm_cols; int P; int chunk; int nsets; int L; int bf;
   const Fp* chal; long long chal_stride; int y_slot, beta_slot, gamma_slot;

@@ -97,6 +97,38 @@ void q_compile_gates(const tb_cs_desc* cs, QProgram* out) {
   finish_program(c, out);
 }
 
+void q_compile_gates_split(const tb_cs_desc* cs, int parts, std::vector<QProgram>* out, std::vector<int>* counts) {
+  // cost of a root = instructions of its stand-alone program; contiguous groups with roughly equal cumulative cost
+  std::vector<size_t> cost(cs->num_constraints);
+  size_t total = 0;
+  for (uint32_t i = 0; i < cs->num_constraints; ++i) {
+    Compiler c(cs); std::vector<char> seen(cs->num_nodes, 0);
+    c.count(cs->constraint_roots[i], seen);
+    Compiler::Opnd o = c.emit(cs->constraint_roots[i]); (void)o;
+    cost[i] = c.code.size() + 1; total += cost[i];
+  }
+  if (parts > (int)cs->num_constraints) parts = cs->num_constraints ? (int)cs->num_constraints : 1;
+  out->clear(); counts->clear();
+  uint32_t r0 = 0; size_t acc = 0;
+  for (int p = 0; p < parts; ++p) {
+    uint32_t r1 = r0;
+    size_t target = total * (p + 1) / parts;
+    while (r1 < cs->num_constraints && (acc < target || p == parts - 1)) acc += cost[r1++];
+    if (p == parts - 1) r1 = cs->num_constraints;
+    Compiler c(cs); std::vector<char> seen(cs->num_nodes, 0);
+    for (uint32_t i = r0; i < r1; ++i) c.count(cs->constraint_roots[i], seen);
+    for (uint32_t i = r0; i < r1; ++i) {
+      Compiler::Opnd o = c.emit(cs->constraint_roots[i]);
+      c.code.push_back(q_make(Q_FOLD_Y, 0, o.kind, o.v, K_CONST, 0));
+      c.release(o);
+    }
+    out->emplace_back();
+    finish_program(c, &out->back());
+    counts->push_back((int)(r1 - r0));
+    r0 = r1;
+  }
+}
+
 void q_compile_lookups(const tb_cs_desc* cs, QProgram* out) {
   Compiler c(cs);
   std::vector<char> seen(cs->num_nodes, 0);
@@ -118,7 +150,9 @@ void q_compile_lookups(const tb_cs_desc* cs, QProgram* out) {
 }
 
 // ---------------------------------------------------------------- interpreter kernel
-__global__ void q_interp_kernel(const QInstr* __restrict__ prog, int ninstr, int nregs, QData d) {
+__global__ void q_interp_kernel(QPartList pl, int nregs, QData d) {
+  const QInstr* __restrict__ prog = pl.prog[blockIdx.z];
+  const int ninstr = pl.ninstr[blockIdx.z];
   extern __shared__ uint4 q_smem[];
   const int T = blockDim.x, tid = threadIdx.x;
   uint4* rlo = q_smem;
@@ -164,20 +198,32 @@ __global__ void q_interp_kernel(const QInstr* __restrict__ prog, int ninstr, int
     rlo[dst * T + tid] = make_uint4(r.l[0], r.l[1], r.l[2], r.l[3]);
     rhi[dst * T + tid] = make_uint4(r.l[4], r.l[5], r.l[6], r.l[7]);
   }
-  if (d.gate_out) st_fe(d.gate_out + (long long)b * d.gate_pstride + row, acc);
+  if (d.gate_out) st_fe(d.gate_out + (long long)blockIdx.z * pl.part_stride + (long long)b * d.gate_pstride + row, acc);
 }
 
-void q_run(Ctx* c, const QProgram& prog, const QData& d, int B) {
+static void q_launch(Ctx* c, const QPartList& pl, int nregs, const QData& d, int B) {
   ProfScope prof_scope(c, PC_QUOT_GATES);
   static bool attr = false;
   if (!attr) { TB_CUDA(cudaFuncSetAttribute(q_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
-  int T = (96 * 1024) / (prog.nregs * 32);
+  int T = (96 * 1024) / (nregs * 32);
   T = T >= 128 ? 128 : (T / 32) * 32;
   TB_REQUIRE(T >= 32, "constraint program register file does not fit shared memory");
   if (d.n < T) T = d.n < 32 ? 32 : d.n;
-  size_t smem = (size_t)prog.nregs * T * 32;
-  q_interp_kernel<<<dim3((d.n + T - 1) / T, B), T, smem, c->stream>>>(prog.dev, prog.ninstr, prog.nregs, d);
+  size_t smem = (size_t)nregs * T * 32;
+  q_interp_kernel<<<dim3((d.n + T - 1) / T, B, pl.nparts), T, smem, c->stream>>>(pl, nregs, d);
   TB_LAUNCH_CHECK(); c->launches++;
+}
+void q_run(Ctx* c, const QProgram& prog, const QData& d, int B) {
+  QPartList pl; memset(&pl, 0, sizeof(pl));
+  pl.prog[0] = prog.dev; pl.ninstr[0] = prog.ninstr; pl.nparts = 1; pl.part_stride = 0;
+  q_launch(c, pl, prog.nregs, d, B);
+}
+void q_run_parts(Ctx* c, const std::vector<QProgram>& progs, QData d, long long part_stride, int B) {
+  QPartList pl; memset(&pl, 0, sizeof(pl));
+  int nregs = 1;
+  pl.nparts = (int)progs.size(); pl.part_stride = part_stride;
+  for (int p = 0; p < pl.nparts; ++p) { pl.prog[p] = progs[p].dev; pl.ninstr[p] = progs[p].ninstr; nregs = nregs > progs[p].nregs ? nregs : progs[p].nregs; }
+  q_launch(c, pl, nregs, d, B);
 }
 
 // ---------------------------------------------------------------- permutation + lookup terms, vanishing division
@@ -190,6 +236,7 @@ __global__ void __launch_bounds__(128) q_finish_kernel(QFinish f) {
   const Fp one = Fp::one();
   const size_t crow = (size_t)f.k1 * n + row;
   Fp acc = ldg_fe(f.gate + (size_t)b * n + row);
+  for (int p = 1; p < f.nparts; ++p) acc = acc * chal[f.ypow_slot + p] + ldg_fe(f.gate + (size_t)p * f.gate_part_stride + (size_t)b * n + row);
   const Fp l0 = ldg_fe(f.l0 + crow), ll = ldg_fe(f.l_last + crow);
   const Fp active = one - (ll + ldg_fe(f.l_blind + crow));
   const Fp* adv = f.adv + (long long)b * f.adv_pstride;
@@ -219,10 +266,10 @@ __global__ void __launch_bounds__(128) q_finish_kernel(QFinish f) {
     }
   }
   for (int l = 0; l < f.L; ++l) {
-    size_t o = (size_t)b * f.lk_pstride + (size_t)l * n;
+    size_t o = (size_t)b * f.lk_pstride + (size_t)l * n, oc = (size_t)b * f.lkc_pstride + (size_t)l * n;
     Fp z = ldg_fe(f.lz + o + row), zn = ldg_fe(f.lz + o + ((row + 1) & nm));
     Fp ap = ldg_fe(f.lpin + o + row), apm = ldg_fe(f.lpin + o + ((row - 1 + n) & nm)), sp = ldg_fe(f.lptab + o + row);
-    Fp a = ldg_fe(f.lkA + o + row), t = ldg_fe(f.lkS + o + row);
+    Fp a = ldg_fe(f.lkA + oc + row), t = ldg_fe(f.lkS + oc + row);
     acc = acc * y + l0 * (one - z);
     acc = acc * y + ll * (z * z - z);
     acc = acc * y + (zn * (ap + beta) * (sp + gamma) - z * (a + beta) * (t + gamma)) * active;

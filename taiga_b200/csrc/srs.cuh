@@ -2,6 +2,7 @@
 // Replaces halo2_proofs `poly::commitment::Params<vesta::Affine>` (EXT) as loaded by SETUP_PARAMS_MAP
 // (taiga_halo2/src/constant.rs:128-139) and its `commit` / `commit_lagrange` methods.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -21,7 +22,8 @@ struct Srs {
   static Srs* load(Ctx* ctx, uint32_t k, const uint8_t* g, const uint8_t* gl, const uint8_t* w, const uint8_t* u) {
     Srs* s = new Srs();
     s->ctx = ctx; s->k = k; s->n = size_t(1) << k;
-    int c = (int)k - 2; if (c < 4) c = 4; if (c > 13) c = 13;  // 13: 4096 buckets per MSM at k = 15 (see msm.cu MSM_FIXED_C)
+    int c = (int)k - 4; if (c < 4) c = 4; if (c > 11) c = 11;  // 11: 1024 buckets per MSM at k = 15 (see msm.cu MSM_FIXED_C)
+    if (const char* e = getenv("TB_FIXED_C")) { int v = atoi(e); if (v >= 4 && v <= 16) c = v; }  // tuning knob for experiments
     s->c = c; s->W = (256 + c - 1) / c;
     size_t n = s->n;
     try {
@@ -55,15 +57,17 @@ struct Srs {
   ~Srs() { cudaFree(g); cudaFree(g_lagrange); cudaFree(tab_g); cudaFree(tab_gl); cudaFree(wu); }
 
   // acc[k] = MSM(scalars_k, basis) + sum_j extras[k][j] * {w, u}[j] via the fixed-base tables (no normalisation)
-  void commit_xyzz(Ctx* c_, bool lagrange, const Fp* scalars, long long stride, int K, const Fp* extras, int n_extra, Xyzz<Fq>* acc) const {
+  void commit_xyzz(Ctx* c_, bool lagrange, const Fp* scalars, long long stride, int K, const Fp* extras, int n_extra, Xyzz<Fq>* acc,
+                   Aff<Fq>* affine_out = nullptr) const {
     MsmConfig cfg; cfg.c = c; cfg.table_windows = W; cfg.table_stride = (int)n + 2; cfg.n_extra = extras ? n_extra : 0; cfg.extra_scalars = extras;
+    cfg.affine_out = affine_out;
     msm_run<Fq, Fp>(c_, scalars, stride, lagrange ? tab_gl : tab_g, 0, (int)n, K, cfg, acc);
   }
   // out[k] = affine(MSM(scalars_k, basis) + blinds[k] * w)      (Params::commit / commit_lagrange)
   void commit(Ctx* c_, bool lagrange, const Fp* scalars, long long stride, int K, const Fp* blinds, Aff<Fq>* out) const {
     DevBuf<Xyzz<Fq>> acc(c_, K);
-    commit_xyzz(c_, lagrange, scalars, stride, K, blinds, 1, acc.get());
-    points_to_affine<Fq>(c_, acc.get(), K, out);
+    commit_xyzz(c_, lagrange, scalars, stride, K, blinds, 1, acc.get(), out);
+    if (((1 << (c - 1)) / 8) > 256) points_to_affine<Fq>(c_, acc.get(), K, out);  // only when the fused reduction was not used
   }
 };
 
