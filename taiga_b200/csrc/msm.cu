@@ -19,8 +19,9 @@ namespace tb {
 
 constexpr int MSM_CHUNK_MAX = 64;  // max entries accumulated by one thread (adaptive: chosen so the accumulation fills the GPU)
 constexpr int MSM_SEG = 8;         // buckets per thread in the running-sum reduction
-constexpr int MSM_FIXED_C = 11;    // fixed-base window: 1024 buckets per MSM, 24 table windows: the bucket reduction is the latency
-                                   // floor of every commitment, 4x fewer buckets beats 20% more (throughput-bound) accumulation adds
+constexpr int MSM_FIXED_C = 13;    // fixed-base window: 4096 buckets per MSM, 20 table windows (measured best of 11/12/13/16 at k = 15)
+constexpr uint32_t MSM_SERIAL_UNITS = 4;    // buckets with <= 4 units are summed by one thread
+constexpr uint32_t MSM_HEAVY_UNITS = 1024;  // buckets with more units than this get a whole CTA (e.g. the top window of a variable-base MSM)
 
 int msm_default_window(int n, bool fixed_tables) {
   if (fixed_tables) return MSM_FIXED_C;
@@ -66,12 +67,15 @@ __global__ void msm_digits_kernel(const S* __restrict__ scalars, long long sstri
   }
 }
 
-// units (chunks of <= chunk entries) per bucket
-__global__ void msm_units_kernel(const uint32_t* __restrict__ offs, uint32_t nb_total, uint32_t chunk_log, uint32_t* __restrict__ unit_count) {
+// units (chunks of <= chunk entries) per bucket; oversized buckets are appended to the heavy list
+__global__ void msm_units_kernel(const uint32_t* __restrict__ offs, uint32_t nb_total, uint32_t chunk_log, uint32_t* __restrict__ unit_count,
+                                 uint32_t* __restrict__ heavy, uint32_t* __restrict__ n_heavy) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb_total) return;
   uint32_t cnt = offs[b + 1] - offs[b];
-  unit_count[b] = (cnt + (1u << chunk_log) - 1) >> chunk_log;
+  uint32_t uc = (cnt + (1u << chunk_log) - 1) >> chunk_log;
+  unit_count[b] = uc;
+  if (uc > MSM_HEAVY_UNITS) heavy[atomicAdd(n_heavy, 1u)] = b;
 }
 
 template <class B>
@@ -127,6 +131,7 @@ __global__ void __launch_bounds__(256) msm_combine_kernel(const uint32_t* __rest
   uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= nb_total) return;
   uint32_t u0 = unit_off[b], u1 = unit_off[b + 1], units = u1 - u0;
+  if (units <= MSM_SERIAL_UNITS || units > MSM_HEAVY_UNITS) return;  // handled by the serial / heavy kernels
   Xyzz<B> acc = Xyzz<B>::inf();
   for (uint32_t u = u0 + lane; u < u1; u += 32) acc.add(partial[u]);
   if (units > 1) {
@@ -143,9 +148,27 @@ __global__ void __launch_bounds__(128) msm_combine_serial_kernel(const uint32_t*
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb_total) return;
   uint32_t u0 = unit_off[b], u1 = unit_off[b + 1];
+  if (u1 - u0 > MSM_SERIAL_UNITS) return;  // handled by the warp / heavy kernels
   Xyzz<B> acc = Xyzz<B>::inf();
   for (uint32_t u = u0; u < u1; ++u) acc.add(partial[u]);
   buckets[b] = acc;
+}
+
+// one CTA per oversized bucket (grid-stride over the heavy list)
+template <class B>
+__global__ void __launch_bounds__(256) msm_combine_heavy_kernel(const uint32_t* __restrict__ heavy, const uint32_t* __restrict__ n_heavy,
+                                                                 const uint32_t* __restrict__ unit_off, const Xyzz<B>* __restrict__ partial,
+                                                                 Xyzz<B>* __restrict__ buckets) {
+  __shared__ Xyzz<B> sm[8];
+  const uint32_t nh = *n_heavy;
+  for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+    uint32_t b = heavy[h], u0 = unit_off[b], u1 = unit_off[b + 1];
+    Xyzz<B> acc = Xyzz<B>::inf();
+    for (uint32_t u = u0 + threadIdx.x; u < u1; u += blockDim.x) acc.add(partial[u]);
+    acc = block_reduce_pt(acc, sm);
+    if (threadIdx.x == 0) buckets[b] = acc;
+    __syncthreads();
+  }
 }
 
 // running-sum reduction of one segment of `seg` buckets: sum_b (b+1) * bucket_b restricted to the segment
@@ -256,8 +279,10 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
   { const uint64_t target_units = 4ull * 512 * (uint64_t)ctx->sm_count;
     while ((1u << chunk_log) < (uint32_t)MSM_CHUNK_MAX && (max_entries >> chunk_log) > target_units) ++chunk_log; }
   const uint64_t max_units = nb_total64 + (max_entries >> chunk_log) + 1;
-  DevBuf<uint32_t> unit_count(ctx, nb_total), unit_off(ctx, nb_total + 1);
-  msm_units_kernel<<<(nb_total + 255) / 256, 256, 0, st>>>(offs.get(), nb_total, chunk_log, unit_count.get());
+  const uint64_t max_heavy = (max_entries >> chunk_log) / MSM_HEAVY_UNITS + 1;
+  DevBuf<uint32_t> unit_count(ctx, nb_total), unit_off(ctx, nb_total + 1), heavy(ctx, max_heavy), n_heavy(ctx, 1);
+  n_heavy.zero();
+  msm_units_kernel<<<(nb_total + 255) / 256, 256, 0, st>>>(offs.get(), nb_total, chunk_log, unit_count.get(), heavy.get(), n_heavy.get());
   TB_LAUNCH_CHECK();
   exclusive_scan_u32(ctx, unit_count.get(), unit_off.get(), nb_total);
   DevBuf<Xyzz<B>> partial(ctx, max_units), buckets(ctx, nb_total);
@@ -266,10 +291,12 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
                                                                           nb_total, 1u << chunk_log, entries.get(), partial.get());
   TB_LAUNCH_CHECK();
   ps.reset(); ps.reset(new ProfScope(ctx, PC_MSM_REDUCE));
-  if ((max_entries >> chunk_log) <= 4 * nb_total64)  // few units per bucket on average: one thread per bucket
-    msm_combine_serial_kernel<B><<<(nb_total + 127) / 128, 128, 0, st>>>(unit_off.get(), partial.get(), nb_total, buckets.get());
-  else
+  // three disjoint classes of buckets: <= 4 units (one thread), <= 1024 units (one warp), more (one CTA each)
+  msm_combine_serial_kernel<B><<<(nb_total + 127) / 128, 128, 0, st>>>(unit_off.get(), partial.get(), nb_total, buckets.get());
+  if ((max_entries >> chunk_log) > MSM_SERIAL_UNITS)
     msm_combine_kernel<B><<<(unsigned)(((uint64_t)nb_total * 32 + 255) / 256), 256, 0, st>>>(unit_off.get(), partial.get(), nb_total, buckets.get());
+  if ((max_entries >> chunk_log) > MSM_HEAVY_UNITS)
+    msm_combine_heavy_kernel<B><<<(unsigned)(max_heavy < 296 ? max_heavy : 296), 256, 0, st>>>(heavy.get(), n_heavy.get(), unit_off.get(), partial.get(), buckets.get());
   TB_LAUNCH_CHECK();
 
   const int seg = NB < MSM_SEG ? NB : MSM_SEG;

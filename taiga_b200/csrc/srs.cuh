@@ -22,7 +22,7 @@ struct Srs {
   static Srs* load(Ctx* ctx, uint32_t k, const uint8_t* g, const uint8_t* gl, const uint8_t* w, const uint8_t* u) {
     Srs* s = new Srs();
     s->ctx = ctx; s->k = k; s->n = size_t(1) << k;
-    int c = (int)k - 4; if (c < 4) c = 4; if (c > 11) c = 11;  // 11: 1024 buckets per MSM at k = 15 (see msm.cu MSM_FIXED_C)
+    int c = (int)k - 2; if (c < 4) c = 4; if (c > 13) c = 13;  // 13: 4096 buckets per MSM at k = 15 (see msm.cu MSM_FIXED_C)
     if (const char* e = getenv("TB_FIXED_C")) { int v = atoi(e); if (v >= 4 && v <= 16) c = v; }  // tuning knob for experiments
     s->c = c; s->W = (256 + c - 1) / c;
     size_t n = s->n;
