@@ -45,6 +45,9 @@ struct FqParams {  // Vesta base field = Pallas scalar field
 };
 
 
+#ifndef TB_NOINLINE_MUL
+#define TB_NOINLINE_MUL 1
+#endif
 #if defined(__CUDA_ARCH__) && !defined(TB_PORTABLE_FIELD)
 #define TB_PTX_FIELD 1
 // One row of the operand-scanning Montgomery product: t[0..8] += a[0..7] * bi.
@@ -208,7 +211,20 @@ struct alignas(16) Fe {
   TB_HD Fe dbl() const { return *this + *this; }
 
   // Montgomery product a*b*R^-1 mod m (CIOS, 32-bit limbs, Pasta-specific reduction row)
+#ifdef TB_PTX_FIELD
+  // Out-of-line Montgomery product.  The EC formulas call the multiply 10-14 times each; fully inlined they are
+  // ~100 KB of SASS per kernel and ncu showed `no_instruction` (instruction-cache miss) as the top stall of the MSM
+  // kernels.  As a real function (operands and result travel in registers) the hot kernels fit the 32 KB L1.5 I-cache.
+  static __device__ __noinline__ Fe mul_call(Fe a, Fe b) { return mul_body(a, b); }
+#endif
   friend TB_HD Fe operator*(const Fe& a, const Fe& b) {
+#if defined(TB_PTX_FIELD) && TB_NOINLINE_MUL
+    return mul_call(a, b);
+#else
+    return mul_body(a, b);
+#endif
+  }
+  static TB_HD Fe mul_body(const Fe& a, const Fe& b) {
 #ifdef TB_PTX_FIELD
     // requires a < m (any 256-bit b): invariant t < 2m after every row, so 9 limbs never overflow
     uint32_t t[9];

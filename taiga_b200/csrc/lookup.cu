@@ -4,6 +4,7 @@
 //   S'_i = A'_i wherever A'_i starts a new run (consuming one copy of that table value); the remaining slots receive
 //   the unused table values in ascending order, handed out from the LAST repeated row backwards (the BTreeMap / pop()
 //   order of the reference), so the result is bit-identical to the CPU path, not merely a valid arrangement.
+#define TB_NOINLINE_MUL 0  // loop-structured kernels: small code, keep the multiply inline
 #include "common.cuh"
 #include "prover.cuh"
 #include "prover_kernels.cuh"

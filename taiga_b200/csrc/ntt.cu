@@ -11,6 +11,7 @@
 // two 16-byte halves (conflict-free LDS.128) with a one-element pad per row.
 //
 // Algorithmic bytes: 64*N per transform (read N*32, write N*32); passes = ceil(logN / 9) for logN > 11.
+#define TB_NOINLINE_MUL 0  // loop-structured kernels: small code, keep the multiply inline
 #include "common.cuh"
 #include "kernels.cuh"
 

@@ -1,4 +1,5 @@
 // Elementwise field-vector kernels and small utilities (exclusive scan) for libtaiga_b200.
+#define TB_NOINLINE_MUL 0  // loop-structured kernels: small code, keep the multiply inline
 #include "common.cuh"
 #include "kernels.cuh"
 

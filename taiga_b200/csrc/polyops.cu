@@ -2,6 +2,7 @@
 // batch inversion, prefix products, inner products, power vectors, and a per-proof scalar interpreter.
 // Replaces halo2_proofs `arithmetic::{eval_polynomial, kate_division, compute_inner_product}`, `BatchInvert` and the
 // `Polynomial` +, * operators used by plonk::create_proof / multiopen / commitment (EXT).
+#define TB_NOINLINE_MUL 0  // loop-structured kernels: small code, keep the multiply inline
 #include "common.cuh"
 #include "prover.cuh"
 

@@ -9,6 +9,7 @@
 //
 // Algorithmic bytes per sub-coset row: 32*(C+1), C = distinct column-cosets read.
 #include <map>
+#define TB_NOINLINE_MUL 0  // loop-structured kernels: small code, keep the multiply inline
 #include "common.cuh"
 #include "prover_kernels.cuh"
 

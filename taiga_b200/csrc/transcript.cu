@@ -8,6 +8,7 @@
 //
 // The blinding PRF replaces the caller's `RngCore` (proof.rs:30): every random scalar of proof i is
 // BLAKE2b-512(personal "TaigaB200-Blind\0", seed || i || tag || index) reduced mod p, reproducible on the CPU oracle.
+#define TB_NOINLINE_MUL 0  // loop-structured kernels: small code, keep the multiply inline
 #include "common.cuh"
 #include "prover.cuh"
 
