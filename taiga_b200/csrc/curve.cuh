@@ -41,44 +41,65 @@ struct alignas(16) Xyzz {
   TB_HD Xyzz dbl() const {
     if (is_inf() || Y.is_zero()) return inf();
     Xyzz r;
-    F U = Y.dbl(), V = U.sqr(), W = U * V, S = X * V;
-    F x2 = X.sqr(), M = x2.dbl() + x2;
+    F U = Y.dbl(), V, x2;
+    F::mul2(U, U, X, X, V, x2);
+    F W, S;
+    F::mul2(U, V, X, V, W, S);
+    F M = x2.dbl() + x2;
     r.X = M.sqr() - S.dbl();
-    r.Y = M * (S - r.X) - W * Y;
-    r.ZZ = V * ZZ; r.ZZZ = W * ZZZ;
+    F t1, t2;
+    F::mul2(M, S - r.X, W, Y, t1, t2);
+    r.Y = t1 - t2;
+    F::mul2(V, ZZ, W, ZZZ, r.ZZ, r.ZZZ);
     return r;
   }
-  // this += affine (madd-2008-s), with all exceptional cases handled
+  // this += affine (madd-2008-s), with all exceptional cases handled; the ten multiplies are issued as five
+  // independent pairs (F::mul2)
   TB_HD void add_affine(const Aff<F>& b) {
     if (b.is_inf()) return;
     if (is_inf()) { *this = from_affine(b); return; }
-    F U2 = b.x * ZZ, S2 = b.y * ZZZ;
+    F U2, S2;
+    F::mul2(b.x, ZZ, b.y, ZZZ, U2, S2);
     F Pp = U2 - X, R = S2 - Y;
     if (Pp.is_zero()) {
       if (R.is_zero()) *this = dbl_affine(b); else *this = inf();
       return;
     }
-    F PP = Pp.sqr(), PPP = Pp * PP, Qq = X * PP;
-    F X3 = R.sqr() - PPP - Qq.dbl();
-    Y = R * (Qq - X3) - Y * PPP;
+    F PP, RR;
+    F::mul2(Pp, Pp, R, R, PP, RR);
+    F PPP, Qq;
+    F::mul2(Pp, PP, X, PP, PPP, Qq);
+    F X3 = RR - PPP - Qq.dbl();
+    F t1, t2;
+    F::mul2(R, Qq - X3, Y, PPP, t1, t2);
+    Y = t1 - t2;
     X = X3;
-    ZZ = ZZ * PP; ZZZ = ZZZ * PPP;
+    F::mul2(ZZ, PP, ZZZ, PPP, ZZ, ZZZ);
   }
-  // this += b (add-2008-s)
+  // this += b (add-2008-s); fourteen multiplies as seven independent pairs
   TB_HD void add(const Xyzz& b) {
     if (b.is_inf()) return;
     if (is_inf()) { *this = b; return; }
-    F U1 = X * b.ZZ, U2 = b.X * ZZ, S1 = Y * b.ZZZ, S2 = b.Y * ZZZ;
+    F U1, U2, S1, S2;
+    F::mul2(X, b.ZZ, b.X, ZZ, U1, U2);
+    F::mul2(Y, b.ZZZ, b.Y, ZZZ, S1, S2);
     F Pp = U2 - U1, R = S2 - S1;
     if (Pp.is_zero()) {
       if (R.is_zero()) *this = dbl(); else *this = inf();
       return;
     }
-    F PP = Pp.sqr(), PPP = Pp * PP, Qq = U1 * PP;
-    F X3 = R.sqr() - PPP - Qq.dbl();
-    Y = R * (Qq - X3) - S1 * PPP;
+    F PP, RR;
+    F::mul2(Pp, Pp, R, R, PP, RR);
+    F PPP, Qq;
+    F::mul2(Pp, PP, U1, PP, PPP, Qq);
+    F X3 = RR - PPP - Qq.dbl();
+    F t1, t2;
+    F::mul2(R, Qq - X3, S1, PPP, t1, t2);
+    Y = t1 - t2;
     X = X3;
-    ZZ = ZZ * b.ZZ * PP; ZZZ = ZZZ * b.ZZZ * PPP;
+    F z2, z3;
+    F::mul2(ZZ, b.ZZ, ZZZ, b.ZZZ, z2, z3);
+    F::mul2(z2, PP, z3, PPP, ZZ, ZZZ);
   }
   TB_HD Xyzz neg() const { Xyzz r = *this; r.Y = Y.neg(); return r; }
   // one field inversion

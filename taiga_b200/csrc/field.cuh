@@ -216,7 +216,38 @@ struct alignas(16) Fe {
   // ~100 KB of SASS per kernel and ncu showed `no_instruction` (instruction-cache miss) as the top stall of the MSM
   // kernels.  As a real function (operands and result travel in registers) the hot kernels fit the 32 KB L1.5 I-cache.
   static __device__ __noinline__ Fe mul_call(Fe a, Fe b) { return mul_body(a, b); }
+  // Two independent products per call: the two carry chains interleave, doubling the instruction-level parallelism of
+  // the (latency-bound) EC formulas, whose multiplies come in independent pairs.
+  struct Pair { Fe a, b; };
+  static __device__ __noinline__ Pair mul2_call(Fe a, Fe b, Fe c, Fe d) {
+    uint32_t t[9], u[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { t[i] = 0; u[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      tb_mul_row(t, a.l, b.l[i]);
+      tb_mul_row(u, c.l, d.l[i]);
+      tb_red_row(t, P::m(1), P::m(2), P::m(3));
+      tb_red_row(u, P::m(1), P::m(2), P::m(3));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { t[j] = t[j + 1]; u[j] = u[j + 1]; }
+      t[8] = 0; u[8] = 0;
+    }
+    Pair r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r.a.l[i] = t[i]; r.b.l[i] = u[i]; }
+    cond_sub(r.a.l); cond_sub(r.b.l);
+    return r;
+  }
 #endif
+  // (x*y, z*w)
+  static TB_HD void mul2(const Fe& x, const Fe& y, const Fe& z, const Fe& w, Fe& r1, Fe& r2) {
+#if defined(TB_PTX_FIELD) && TB_NOINLINE_MUL
+    Pair p = mul2_call(x, y, z, w); r1 = p.a; r2 = p.b;
+#else
+    r1 = x * y; r2 = z * w;
+#endif
+  }
   friend TB_HD Fe operator*(const Fe& a, const Fe& b) {
 #if defined(TB_PTX_FIELD) && TB_NOINLINE_MUL
     return mul_call(a, b);

@@ -40,17 +40,23 @@ class Proof:
 
 
 class ProverService:
-    """SRS + Compliance / Resource-Logic proving keys resident on one GPU."""
+    """SRS + Compliance / Resource-Logic proving keys resident on one GPU.
 
-    def __init__(self, device=0, srs_arrays=None):
-        self.ctx = lib.Context(device)
-        self.ctx2 = lib.Context(device)   # second stream: the VP batch overlaps the Compliance batch
+    `c_workers` / `v_workers` independent (context = CUDA stream, proving key) pairs per circuit: the proofs of a batch
+    are split among them and proved concurrently, so the latency-bound phases of one proof (transcript, bucket
+    reductions, IPA rounds) overlap with the throughput-bound phases of the others.  For large batches one worker per
+    circuit is enough (the kernels already fill the GPU)."""
+
+    def __init__(self, device=0, srs_arrays=None, c_workers=2, v_workers=2):
         s = srs_arrays
+        self.ctx = lib.Context(device)
         self.srs = self.ctx.load_srs(s["k"], s["g"], s["g_lagrange"], s["w"], s["u"])
         self.kd_c, self.make_c = circuits_taiga.build(True)
         self.kd_v, self.make_v = circuits_taiga.build(False)
-        self.pk_c = self.srs.load_circuit(self.kd_c)
-        self.pk_v = self.srs.load_circuit(self.kd_v)
+        self.c_workers = [(self.ctx if i == 0 else lib.Context(device), self.srs.load_circuit(self.kd_c)) for i in range(c_workers)]
+        self.v_workers = [(lib.Context(device), self.srs.load_circuit(self.kd_v)) for _ in range(v_workers)]
+        self.pk_c, self.pk_v = self.c_workers[0][1], self.v_workers[0][1]
+        self.contexts = [w[0] for w in self.c_workers + self.v_workers]
 
     def synthesize_ptx(self, n_ptx, wseed=0):
         """Witness tables for n_ptx partial transactions: dict of stacked numpy arrays (host)."""
@@ -66,37 +72,60 @@ class ProverService:
         c_adv / v_adv may override the advice buffers (e.g. pinned host or device-resident torch tensors)."""
         c_adv = wit["c_adv"] if c_adv is None else c_adv
         v_adv = wit["v_adv"] if v_adv is None else v_adv
-        res = {}
+        jobs = []   # (result slot, worker, first proof, last proof, ...)
+        for kind, workers, adv, inst, lens, index0 in (("c", self.c_workers, c_adv, wit["c_inst"], wit["c_len"], 0),
+                                                       ("v", self.v_workers, v_adv, wit["v_inst"], wit["v_len"], 1 << 20)):
+            total = len(inst)
+            nw = min(len(workers), total)
+            for w in range(nw):
+                lo, hi = total * w // nw, total * (w + 1) // nw
+                jobs.append((kind, lo, hi, workers[w], adv, inst, lens, index0))
+        results, errors = {}, []
 
-        def run_vp():
+        def run(job):
+            kind, lo, hi, (ctx, pk), adv, inst, lens, index0 = job
             try:
-                res["vp"] = self._prove_chunks(self.pk_v, v_adv, wit["v_inst"], wit["v_len"], seed, max_batch, 1 << 20, self.ctx2)
+                results[(kind, lo)] = self._prove_range(pk, ctx, adv, inst, lens, seed, max_batch, index0, lo, hi)
             except BaseException as ex:  # re-raised in the caller's thread
-                res["err"] = ex
-        th = threading.Thread(target=run_vp)
-        th.start()   # ctypes releases the GIL inside tb_prove_batch, so both batches are enqueued concurrently on two streams
-        cp = self._prove_chunks(self.pk_c, c_adv, wit["c_inst"], wit["c_len"], seed, max_batch, 0, self.ctx)
-        th.join()
-        if "err" in res:
-            raise res["err"]
-        return cp, res["vp"]
+                errors.append(ex)
+        threads = [threading.Thread(target=run, args=(j,)) for j in jobs[1:]]
+        for th in threads:
+            th.start()   # ctypes releases the GIL inside tb_prove_batch: every worker enqueues on its own stream
+        run(jobs[0])
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
+        out = {"c": [], "v": []}
+        for (kind, lo) in sorted(results):
+            out[kind] += results[(kind, lo)]
+        return out["c"], out["v"]
 
     @property
     def launch_count(self):
-        return self.ctx.launch_count + self.ctx2.launch_count
+        return sum(c.launch_count for c in self.contexts)
+
+    def prof_enable(self, on=True):
+        for c in self.contexts:
+            c.prof_enable(on)
+
+    def prof_read(self):
+        tot = {}
+        for c in self.contexts:
+            for k_, v_ in c.prof_read().items():
+                a = tot.get(k_, (0.0, 0))
+                tot[k_] = (a[0] + v_[0], a[1] + v_[1])
+        return tot
 
     @staticmethod
-    def _prove_chunks(pk, adv, inst, lens, seed, max_batch, index0, ctx):
+    def _prove_range(pk, ctx, adv, inst, lens, seed, max_batch, index0, lo, hi):
         kd = pk.keydata
         per = kd.cs.num_advice * kd.n * 32
-        if hasattr(adv, "data_ptr"):  # torch tensor (pinned host or device)
-            total = adv.numel() // per
-        else:
-            total = adv.size // per
+        total = len(inst)
         out = []
-        for s in range(0, total, max_batch):
-            e = min(total, s + max_batch)
-            if hasattr(adv, "data_ptr"):
+        for s in range(lo, hi, max_batch):
+            e = min(hi, s + max_batch)
+            if hasattr(adv, "data_ptr"):  # torch tensor (pinned host or device)
                 chunk = _TensorSlice(adv, s * per, (e - s) * per)
             else:
                 chunk = adv.reshape(total, -1)[s:e]
