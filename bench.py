@@ -185,6 +185,14 @@ def sweep(ctx, hbm_peak, quick):
     return out
 
 
+# DRAM traffic per launch of the dominant kernels from the committed ncu captures (profiles/r01_ncu_summary.md, capture B:
+# Compliance-shaped circuit, 2 proofs per launch = 20 advice MSMs resp. one sub-coset of 2 proofs)
+NCU_TRAFFIC = {
+    "msm_accum": {"dram_bytes_per_launch": 48.6e6, "algorithmic_bytes_same_launch": 20 * 96 * N15, "capture": "profiles/r01_ncu_summary.md capture B (K = 20 MSMs)"},
+    "quotient_gates": {"dram_bytes_per_launch": 40.6e6, "algorithmic_bytes_same_launch": 2 * 32 * 31 * N15, "capture": "profiles/r01_ncu_summary.md capture B (one sub-coset, 2 proofs)"},
+    "ntt": {"dram_bytes_per_launch": 21.2e6, "algorithmic_bytes_same_launch": 20 * 32 * N15, "capture": "profiles/r01_ncu_summary.md capture A (one pass, 20 columns: read 21 MB = algorithmic)"},
+}
+
 ALG_BYTES_NOTE = {
     "ntt": "64*n per size-n transform (read + write once)",
     "msm_accum": "96 B per MSM term (64 B affine base + 32 B scalar), SURVEY 8d",
@@ -204,6 +212,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--full-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--batch-probe", type=int, default=8, help="also time a batch of this many ptx per step (0 = off)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -315,6 +324,11 @@ def main():
     if top_bytes:
         roof["achieved"] = round(top_bytes / (top_ms * 1e-3) / 1e9, 2)
         roof["frac"] = round(roof["achieved"] / hbm_peak, 5)
+    if top_name in NCU_TRAFFIC:
+        roof["traffic"] = NCU_TRAFFIC[top_name]
+    # the same figures for every kernel group of the step (the dominant one is repeated above)
+    roof["per_kernel"] = {k: {"ms": round(v[0], 3), "groups": v[1], "achieved_gbs": (round(alg[k] / (v[0] * 1e-3) / 1e9, 2) if alg.get(k) and v[0] > 0 else None),
+                              "frac": (round(alg[k] / (v[0] * 1e-3) / 1e9 / hbm_peak, 5) if alg.get(k) and v[0] > 0 else None)} for k, v in prof.items()}
     line = {
         "metric": "partial-tx proofs/sec", "value": round(value, 4), "unit": "ptx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dev_step_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -330,6 +344,23 @@ def main():
         "profile_ms": {k: round(v[0], 3) for k, v in prof.items()},
         "kernel_time_over_step_time": round(tot_prof / dev_step_ms, 3),
     }
+    if args.batch_probe and world == 1 and P == 1:
+        # BASELINE configs[2]-style throughput probe: the same six witnesses tiled to `batch_probe` ptx (distinct blinding seeds per
+        # proof, so distinct proofs), device resident, one stream per circuit
+        bp = args.batch_probe
+        wit_b = {k_: (np.concatenate([v_] * bp) if k_.endswith(("_adv", "_inst")) else v_) for k_, v_ in wit.items()}
+        cb, vb = torch.from_numpy(wit_b["c_adv"]).cuda(), torch.from_numpy(wit_b["v_adv"]).cuda()
+        svc.build_ptx_batch(wit_b, seed0, cb, vb)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        reps = 2
+        for i in range(reps):
+            svc.build_ptx_batch(wit_b, bytes((b + 7 + i) & 0xFF for b in seed0), cb, vb)
+        torch.cuda.synchronize()
+        dt = (time.time() - t0) / reps
+        line["batch_probe"] = {"ptx_per_step": bp, "value": round(bp / dt, 3), "unit": "ptx/s", "ms_per_step": round(dt * 1e3, 2),
+                               "note": "device-resident, witnesses of the P=1 step tiled %dx (distinct seeds)" % bp}
+        del cb, vb
     if not args.no_sweep and world == 1:
         line["sweeps"] = sweep(ctx, hbm_peak, quick=not args.full_sweep)
     if not args.no_cpu:
