@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--full-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="one stream, no threads (for ncu launch lists; not a benchmark configuration)")
     ap.add_argument("--batch-probe", type=int, default=8, help="also time a batch of this many ptx per step (0 = off)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -227,7 +228,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     srs = load_srs()
     nw = 2 if args.ptx <= 2 else 1   # small batches: two streams per circuit so latency-bound phases overlap
-    svc = ptx.ProverService(local, srs, c_workers=nw, v_workers=nw)
+    if args.serial:
+        nw = 1
+    svc = ptx.ProverService(local, srs, c_workers=nw, v_workers=nw, serial=args.serial)
     ctx = svc.ctx
     P = args.ptx
     wit = svc.synthesize_ptx(P, wseed=rank)

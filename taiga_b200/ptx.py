@@ -47,8 +47,9 @@ class ProverService:
     reductions, IPA rounds) overlap with the throughput-bound phases of the others.  For large batches one worker per
     circuit is enough (the kernels already fill the GPU)."""
 
-    def __init__(self, device=0, srs_arrays=None, c_workers=2, v_workers=2):
+    def __init__(self, device=0, srs_arrays=None, c_workers=2, v_workers=2, serial=False):
         s = srs_arrays
+        self.serial = serial   # prove the jobs one after the other on the calling thread (profiling under ncu)
         self.ctx = lib.Context(device)
         self.srs = self.ctx.load_srs(s["k"], s["g"], s["g_lagrange"], s["w"], s["u"])
         self.kd_c, self.make_c = circuits_taiga.build(True)
@@ -88,12 +89,16 @@ class ProverService:
                 results[(kind, lo)] = self._prove_range(pk, ctx, adv, inst, lens, seed, max_batch, index0, lo, hi)
             except BaseException as ex:  # re-raised in the caller's thread
                 errors.append(ex)
-        threads = [threading.Thread(target=run, args=(j,)) for j in jobs[1:]]
-        for th in threads:
-            th.start()   # ctypes releases the GIL inside tb_prove_batch: every worker enqueues on its own stream
-        run(jobs[0])
-        for th in threads:
-            th.join()
+        if self.serial:
+            for j in jobs:
+                run(j)
+        else:
+            threads = [threading.Thread(target=run, args=(j,)) for j in jobs[1:]]
+            for th in threads:
+                th.start()   # ctypes releases the GIL inside tb_prove_batch: every worker enqueues on its own stream
+            run(jobs[0])
+            for th in threads:
+                th.join()
         if errors:
             raise errors[0]
         out = {"c": [], "v": []}
