@@ -127,11 +127,11 @@ template <class B> __device__ Xyzz<B> block_reduce_pt(Xyzz<B> v, Xyzz<B>* sm /* 
 // one warp per bucket: sum the partial results of its units into a dense bucket array (warp-shuffle tree, only as deep as needed)
 template <class B>
 __global__ void __launch_bounds__(256) msm_combine_kernel(const uint32_t* __restrict__ unit_off, const Xyzz<B>* __restrict__ partial, uint32_t nb_total,
-                                                           Xyzz<B>* __restrict__ buckets) {
+                                                           uint32_t serial_units, Xyzz<B>* __restrict__ buckets) {
   uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= nb_total) return;
   uint32_t u0 = unit_off[b], u1 = unit_off[b + 1], units = u1 - u0;
-  if (units <= MSM_SERIAL_UNITS || units > MSM_HEAVY_UNITS) return;  // handled by the serial / heavy kernels
+  if ((serial_units && units <= serial_units) || units > MSM_HEAVY_UNITS) return;  // handled by the serial / heavy kernels
   Xyzz<B> acc = Xyzz<B>::inf();
   for (uint32_t u = u0 + lane; u < u1; u += 32) acc.add(partial[u]);
   if (units > 1) {
@@ -291,11 +291,14 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
                                                                           nb_total, 1u << chunk_log, entries.get(), partial.get());
   TB_LAUNCH_CHECK();
   ps.reset(); ps.reset(new ProfScope(ctx, PC_MSM_REDUCE));
-  // three disjoint classes of buckets: <= 4 units (one thread), <= 1024 units (one warp), more (one CTA each)
-  msm_combine_serial_kernel<B><<<(nb_total + 127) / 128, 128, 0, st>>>(unit_off.get(), partial.get(), nb_total, buckets.get());
-  if ((max_entries >> chunk_log) > MSM_SERIAL_UNITS)
-    msm_combine_kernel<B><<<(unsigned)(((uint64_t)nb_total * 32 + 255) / 256), 256, 0, st>>>(unit_off.get(), partial.get(), nb_total, buckets.get());
-  if ((max_entries >> chunk_log) > MSM_HEAVY_UNITS)
+  // three disjoint classes of buckets: <= 4 units (one thread), <= 1024 units (one warp), more (one CTA each).
+  // Small problems (latency matters, lanes are free) let the warp kernel take the first class too: one launch less.
+  const bool warp_only = nb_total64 <= (64u << 10);
+  if (!warp_only) msm_combine_serial_kernel<B><<<(nb_total + 127) / 128, 128, 0, st>>>(unit_off.get(), partial.get(), nb_total, buckets.get());
+  if (warp_only || (max_entries >> chunk_log) > MSM_SERIAL_UNITS)
+    msm_combine_kernel<B><<<(unsigned)(((uint64_t)nb_total * 32 + 255) / 256), 256, 0, st>>>(unit_off.get(), partial.get(), nb_total,
+                                                                                              warp_only ? 0u : MSM_SERIAL_UNITS, buckets.get());
+  if ((max_entries >> chunk_log) > MSM_HEAVY_UNITS)  // e.g. the top window of a variable-base MSM, or a witness column that is mostly ones
     msm_combine_heavy_kernel<B><<<(unsigned)(max_heavy < 296 ? max_heavy : 296), 256, 0, st>>>(heavy.get(), n_heavy.get(), unit_off.get(), partial.get(), buckets.get());
   TB_LAUNCH_CHECK();
 

@@ -336,14 +336,17 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   Transcripts tr; tr.init(ctx, B, C.proof_len, C.vk_repr);
   WBuf<Fp> scratch = ws.buf<Fp>((size_t)B * std::max({NC, (int)C.pieces, 4}) * n);
   WBuf<Fp> polys = ws.buf<Fp>((size_t)B * NC * n), cosets = ws.buf<Fp>((size_t)B * NC * n);
-  WBuf<Aff<Fq>> pts = ws.buf<Aff<Fq>>((size_t)B * std::max({na, ni1, 2 * L1, ns1, (int)C.pieces, 2}));
-  WBuf<Fp> blinds = ws.buf<Fp>((size_t)B * std::max({na, ni1, L1, ns1, (int)C.pieces, 4}));
+  WBuf<Aff<Fq>> pts = ws.buf<Aff<Fq>>((size_t)B * std::max({na + ni, 2 * L1, ns1 + L1, (int)C.pieces, 2}));
+  WBuf<Fp> blinds = ws.buf<Fp>((size_t)B * std::max({na + ni, 2 * L1, ns1 + L1, (int)C.pieces, 4}));
   WBuf<uint32_t> derr = ws.buf<uint32_t>(1); derr.zero();
 
-  // ---- instance columns: pad, commit_lagrange(Blind::default() = 1) -> common_point, iNTT
-  WBuf<Fp> inst_vals = ws.buf<Fp>((size_t)B * ni1 * n);
+  // ---- instance + advice columns (commit_lagrange): one batched fixed-base MSM call for both
+  // (the vanishing argument's random polynomial is committed over `g`, a different table: separate call)
+  WBuf<Fp> first = ws.buf<Fp>((size_t)B * (ni + na) * n);
+  WBuf<Fp> inst_vals; inst_vals.p = first.get(); inst_vals.n = (size_t)B * ni * n; inst_vals.ctx = ctx;
+  WBuf<Fp> adv_vals; adv_vals.p = first.get() + (size_t)B * ni * n; adv_vals.n = (size_t)B * na * n; adv_vals.ctx = ctx;
   Fp* const inst_polys = polys.get() + (size_t)O_INST * n;
-  inst_vals.zero();
+  if (ni) inst_vals.zero();
   if (ni) {
     size_t off = 0;
     for (int c = 0; c < ni; ++c) {
@@ -354,26 +357,28 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
     }
     fe_to_mont<Fp>(ctx, inst_vals.get(), (size_t)B * ni * n);
     fill_const_kernel<<<(B * ni + 63) / 64, 64, 0, st>>>(blinds.get(), (size_t)B * ni, Fp::one());
-    srs.commit(ctx, true, inst_vals.get(), nn, B * ni, blinds.get(), pts.get());
-    tr.points(pts.get(), ni, ni, false);
-    ntt_run<Fp>(ctx, k, true, inst_vals.get(), inst_polys, scratch.get(), ni, nn, nn, nullptr, nullptr, B, (long long)ni * nn, PS);
   }
   // ---- advice columns: upload, blinding rows, commit, iNTT
-  WBuf<Fp> adv_vals = ws.buf<Fp>((size_t)B * na * n);
   Fp* const adv_polys = polys.get() + (size_t)O_ADV * n;
   TB_CUDA(cudaMemcpyAsync(adv_vals.get(), advice_host, (size_t)B * na * n * 32, cudaMemcpyDefault, st));  // host or device pointer
   fe_to_mont<Fp>(ctx, adv_vals.get(), (size_t)B * na * n);
   for (int c = 0; c < na; ++c)
     prf_fill(ctx, seed, proof0, R_ADVICE_ROWS, (uint32_t)(c * (bf + 1)), adv_vals.get() + (size_t)c * n + C.usable, (long long)na * nn, 1, bf + 1, B);
   prf_fill(ctx, seed, proof0, R_ADVICE_BLIND, 0, VP(V_ADV_BLIND), NV, 1, na, B);
-  poly_copy(ctx, blinds.get(), na, VP(V_ADV_BLIND), NV, na, B);
-  srs.commit(ctx, true, adv_vals.get(), nn, B * na, blinds.get(), pts.get());
-  tr.points(pts.get(), na, na, true);
+  poly_copy(ctx, blinds.get() + (size_t)B * ni, na, VP(V_ADV_BLIND), NV, na, B);
+  srs.commit(ctx, true, first.get(), nn, B * (ni + na), blinds.get(), pts.get());   // [B*ni instance | B*na advice]
+  if (ni) {
+    tr.points(pts.get(), ni, ni, false);
+    ntt_run<Fp>(ctx, k, true, inst_vals.get(), inst_polys, scratch.get(), ni, nn, nn, nullptr, nullptr, B, (long long)ni * nn, PS);
+  }
+  tr.points(pts.get() + (size_t)B * ni, na, na, true);
   ntt_run<Fp>(ctx, k, true, adv_vals.get(), adv_polys, scratch.get(), na, nn, nn, nullptr, nullptr, B, (long long)na * nn, PS);
   tr.squeeze(VP(V_THETA), NV, 1);
 
   // ---- lookups: compress (Lagrange domain), sort, arrange, blind, commit A', S'
-  WBuf<Fp> lkA = ws.buf<Fp>((size_t)B * L1 * n), lkS = ws.buf<Fp>((size_t)B * L1 * n), lpin = ws.buf<Fp>((size_t)B * L1 * n), lptab = ws.buf<Fp>((size_t)B * L1 * n);
+  WBuf<Fp> lkA = ws.buf<Fp>((size_t)B * L1 * n), lkS = ws.buf<Fp>((size_t)B * L1 * n), lperm = ws.buf<Fp>((size_t)2 * B * L1 * n);
+  WBuf<Fp> lpin; lpin.p = lperm.get(); lpin.n = (size_t)B * L1 * n; lpin.ctx = ctx;
+  WBuf<Fp> lptab; lptab.p = lperm.get() + (size_t)B * L * n; lptab.n = (size_t)B * L1 * n; lptab.ctx = ctx;   // adjacent: one commitment call
   Fp* const lpin_polys = polys.get() + (size_t)O_LPIN * n; Fp* const lptab_polys = polys.get() + (size_t)O_LPTAB * n;
   QData qd; memset(&qd, 0, sizeof(qd));
   qd.aq = C.d_aq; qd.fq = C.d_fq; qd.iq = C.d_iq; qd.consts = C.consts; qd.chal = vars.get(); qd.chal_stride = NV; qd.y_slot = V_Y; qd.theta_slot = V_THETA;
@@ -398,12 +403,10 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
     prf_fill(ctx, seed, proof0, R_LK_IN_BLIND, 0, VP(V_LPIN_BLIND), NV, 1, L, B);
     prf_fill(ctx, seed, proof0, R_LK_TAB_BLIND, 0, VP(V_LPTAB_BLIND), NV, 1, L, B);
     // commit in transcript order: per lookup A' then S'
-    WBuf<Aff<Fq>> pa = ws.buf<Aff<Fq>>((size_t)B * L), ps = ws.buf<Aff<Fq>>((size_t)B * L);
     poly_copy(ctx, blinds.get(), L, VP(V_LPIN_BLIND), NV, L, B);
-    srs.commit(ctx, true, lpin.get(), nn, B * L, blinds.get(), pa.get());
-    poly_copy(ctx, blinds.get(), L, VP(V_LPTAB_BLIND), NV, L, B);
-    srs.commit(ctx, true, lptab.get(), nn, B * L, blinds.get(), ps.get());
-    for (int l = 0; l < L; ++l) { tr.points(pa.get() + l, L, 1, true); tr.points(ps.get() + l, L, 1, true); }
+    poly_copy(ctx, blinds.get() + (size_t)B * L, L, VP(V_LPTAB_BLIND), NV, L, B);
+    srs.commit(ctx, true, lperm.get(), nn, 2 * B * L, blinds.get(), pts.get());   // [B*L A' | B*L S']
+    for (int l = 0; l < L; ++l) { tr.points(pts.get() + l, L, 1, true); tr.points(pts.get() + (size_t)B * L + l, L, 1, true); }
     ntt_run<Fp>(ctx, k, true, lpin.get(), lpin_polys, scratch.get(), L, nn, nn, nullptr, nullptr, B, (long long)L * nn, PS);
     ntt_run<Fp>(ctx, k, true, lptab.get(), lptab_polys, scratch.get(), L, nn, nn, nullptr, nullptr, B, (long long)L * nn, PS);
   }
@@ -413,7 +416,8 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   // ---- permutation grand products
   Fp* const pz_polys = polys.get() + (size_t)O_PZ * n;
   const size_t gp = (size_t)std::max(ns1, L1);
-  WBuf<Fp> gnum = ws.buf<Fp>((size_t)B * gp * n), gden = ws.buf<Fp>((size_t)B * gp * n), gz = ws.buf<Fp>((size_t)B * gp * n);
+  WBuf<Fp> gnum = ws.buf<Fp>((size_t)B * gp * n), gden = ws.buf<Fp>((size_t)B * gp * n), gz = ws.buf<Fp>((size_t)B * (ns1 + L1) * n);
+  Fp* const gz_lk = gz.get() + (size_t)B * nsets * n;   // lookup Z vectors directly after the permutation Z vectors: one commitment call
   if (nsets) {
     PermFrac pf; memset(&pf, 0, sizeof(pf));
     pf.adv = adv_vals.get(); pf.adv_pstride = (long long)na * nn; pf.inst = inst_vals.get(); pf.inst_pstride = (long long)ni1 * nn; pf.fix = C.fixed_vals;
@@ -429,9 +433,6 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
       prf_fill(ctx, seed, proof0, R_PERM_ROWS, (uint32_t)(s * bf), gz.get() + (size_t)s * n + (n - bf), (long long)nsets * nn, 1, bf, B);
     prf_fill(ctx, seed, proof0, R_PERM_BLIND, 0, VP(V_PZ_BLIND), NV, 1, nsets, B);
     poly_copy(ctx, blinds.get(), nsets, VP(V_PZ_BLIND), NV, nsets, B);
-    srs.commit(ctx, true, gz.get(), nn, B * nsets, blinds.get(), pts.get());
-    tr.points(pts.get(), nsets, nsets, true);
-    ntt_run<Fp>(ctx, k, true, gz.get(), pz_polys, scratch.get(), nsets, nn, nn, nullptr, nullptr, B, (long long)nsets * nn, PS);
   }
   // ---- lookup grand products
   Fp* const lz_polys = polys.get() + (size_t)O_LZ * n;
@@ -439,14 +440,22 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
     lookup_fractions(ctx, lkA.get(), lkS.get(), lpin.get(), lptab.get(), gnum.get(), gden.get(), (long long)L * nn, L, (int)n, vars.get(), NV, V_BETA, V_GAMMA, B);
     batch_inverse(ctx, gden.get(), (size_t)B * L * n);
     vec_mul(ctx, gnum.get(), gden.get(), (size_t)B * L * n);
-    prefix_product(ctx, gz.get(), gnum.get(), (int)n, B * L);
+    prefix_product(ctx, gz_lk, gnum.get(), (int)n, B * L);
     for (int l = 0; l < L; ++l)
-      prf_fill(ctx, seed, proof0, R_LKZ_ROWS, (uint32_t)(l * bf), gz.get() + (size_t)l * n + (n - bf), (long long)L * nn, 1, bf, B);
+      prf_fill(ctx, seed, proof0, R_LKZ_ROWS, (uint32_t)(l * bf), gz_lk + (size_t)l * n + (n - bf), (long long)L * nn, 1, bf, B);
     prf_fill(ctx, seed, proof0, R_LKZ_BLIND, 0, VP(V_LZ_BLIND), NV, 1, L, B);
-    poly_copy(ctx, blinds.get(), L, VP(V_LZ_BLIND), NV, L, B);
-    srs.commit(ctx, true, gz.get(), nn, B * L, blinds.get(), pts.get());
-    tr.points(pts.get(), L, L, true);
-    ntt_run<Fp>(ctx, k, true, gz.get(), lz_polys, scratch.get(), L, nn, nn, nullptr, nullptr, B, (long long)L * nn, PS);
+    poly_copy(ctx, blinds.get() + (size_t)B * nsets, L, VP(V_LZ_BLIND), NV, L, B);
+  }
+  if (nsets + L) {
+    srs.commit(ctx, true, gz.get(), nn, B * (nsets + L), blinds.get(), pts.get());   // [B*nsets permutation Z | B*L lookup Z]
+    if (nsets) {
+      tr.points(pts.get(), nsets, nsets, true);
+      ntt_run<Fp>(ctx, k, true, gz.get(), pz_polys, scratch.get(), nsets, nn, nn, nullptr, nullptr, B, (long long)nsets * nn, PS);
+    }
+    if (L) {
+      tr.points(pts.get() + (size_t)B * nsets, L, L, true);
+      ntt_run<Fp>(ctx, k, true, gz_lk, lz_polys, scratch.get(), L, nn, nn, nullptr, nullptr, B, (long long)L * nn, PS);
+    }
   }
   // ---- vanishing argument: random polynomial
   WBuf<Fp> random_poly = ws.buf<Fp>((size_t)B * n);
