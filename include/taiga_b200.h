@@ -126,6 +126,9 @@ tb_status tb_circuit_load(tb_ctx* ctx, const tb_srs* srs, const tb_cs_desc* cs, 
                           tb_pk** out);
 void tb_pk_free(tb_pk* pk);
 size_t tb_pk_proof_len(const tb_pk* pk);
+/* keygen_vk on the device (constant.rs:150): commit_lagrange(column, Blind::default()) of every fixed column and of every
+ * permutation sigma column, as 64-byte affine points (vk.fixed_commitments, vk.permutation.commitments). */
+tb_status tb_pk_commitments(tb_ctx* ctx, const tb_pk* pk, uint8_t* fixed_commitments, uint8_t* sigma_commitments);
 tb_status tb_prove_batch(tb_ctx* ctx, const tb_pk* pk, uint32_t n_proofs, const uint8_t* advice, const uint8_t* instance,
                          const uint32_t* instance_len, const uint8_t seed[32], uint32_t first_proof_index, uint8_t* proofs_out,
                          size_t proof_stride);

@@ -672,6 +672,28 @@ tb_status tb_circuit_load(tb_ctx* ctx, const tb_srs* srs, const tb_cs_desc* cs, 
   TB_API_END(ctx)
 }
 void tb_pk_free(tb_pk* pk) { delete reinterpret_cast<Circuit*>(pk); }
+
+// keygen_vk on the device: commit_lagrange(column, Blind::default() = 1) of every fixed and sigma column
+tb_status tb_pk_commitments(tb_ctx* ctx, const tb_pk* pk, uint8_t* fixed_commitments, uint8_t* sigma_commitments) {
+  TB_API_BEGIN(ctx)
+  const Circuit* C = reinterpret_cast<const Circuit*>(pk);
+  TB_REQUIRE(C && (fixed_commitments || C->nf == 0) && (sigma_commitments || C->P == 0), "tb_pk_commitments arguments");
+  TB_CUDA(cudaSetDevice(ctx->c.device));
+  Ctx* c = &ctx->c;
+  for (int which = 0; which < 2; ++which) {
+    int cnt = which ? (int)C->P : (int)C->nf;
+    if (!cnt) continue;
+    DevBuf<Fp> ones(c, cnt);
+    DevBuf<Aff<Fq>> pts(c, cnt);
+    std::vector<Fp> h(cnt, Fp::one());
+    ones.upload(h.data(), cnt);
+    C->srs->commit(c, true, which ? C->sig_vals : C->fixed_vals, (long long)C->n, cnt, ones.get(), pts.get());
+    fe_from_mont<Fq>(c, reinterpret_cast<Fq*>(pts.get()), 2 * (size_t)cnt);
+    pts.download(which ? sigma_commitments : fixed_commitments, cnt);
+    c->sync();
+  }
+  TB_API_END(ctx)
+}
 size_t tb_pk_proof_len(const tb_pk* pk) { return pk ? reinterpret_cast<const Circuit*>(pk)->proof_len : 0; }
 
 tb_status tb_prove_batch(tb_ctx* ctx, const tb_pk* pk, uint32_t n_proofs, const uint8_t* advice, const uint8_t* instance, const uint32_t* instance_len,

@@ -53,6 +53,7 @@ _SIGS = {
     "tb_circuit_load": (_i, [_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
     "tb_pk_free": (None, [_vp]),
     "tb_pk_proof_len": (_sz, [_vp]),
+    "tb_pk_commitments": (_i, [_vp, _vp, _vp, _vp]),
     "tb_prove_batch": (_i, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _u32, _vp, _sz]),
 }
 
@@ -223,6 +224,14 @@ class ProvingKey:
         self.ctx._check(self.ctx._lib.tb_circuit_load(self.ctx._h, srs._h, ctypes.byref(keydata.desc), _ptr(self._fixed), _ptr(self._sigma), ctypes.byref(h)))
         self._h = h
         self.proof_len = int(self.ctx._lib.tb_pk_proof_len(h))
+
+    def commitments(self):
+        """keygen_vk: (fixed column commitments [num_fixed, 64], sigma commitments [P, 64])."""
+        kd = self.keydata
+        f = np.zeros((max(1, kd.cs.num_fixed), 64), np.uint8)
+        s = np.zeros((max(1, len(kd.cs.perm_columns)), 64), np.uint8)
+        self.ctx._check(self.ctx._lib.tb_pk_commitments(self.ctx._h, self._h, _ptr(f), _ptr(s)))
+        return f[: kd.cs.num_fixed], s[: len(kd.cs.perm_columns)]
 
     def prove_batch(self, advice, instance, instance_len, seed, first_proof_index=0):
         """Proof::create for a batch: advice uint8 [B, num_advice, n, 32]; instance uint8 [B, sum(instance_len), 32].

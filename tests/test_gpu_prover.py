@@ -54,3 +54,12 @@ def test_unsatisfied_lookup_is_reported(gpu_ctx, oracle_cpu):
         pk.prove_batch(adv[None], inst[None], lens, bytes(32))
     with pytest.raises(RuntimeError):
         oracle_cpu.OracleKey(kd, srs).prove(adv, inst, lens, bytes(32))
+
+
+def test_keygen_commitments_match_oracle(gpu_ctx, oracle_cpu):
+    """keygen_vk on the device: fixed / sigma column commitments equal the oracle's (vk.fixed_commitments, permutation commitments)."""
+    kd, _ = cm.standard_plonk(k=7, wide=True, n_lookups=1)
+    srs, gsrs = small_srs(oracle_cpu, gpu_ctx, 7)
+    of, os_ = oracle_cpu.OracleKey(kd, srs).commitments()
+    gf, gs = gsrs.load_circuit(kd).commitments()
+    assert gf.tobytes() == of.tobytes() and gs.tobytes() == os_.tobytes()
