@@ -133,6 +133,13 @@ tb_status tb_prove_batch(tb_ctx* ctx, const tb_pk* pk, uint32_t n_proofs, const 
                          const uint32_t* instance_len, const uint8_t seed[32], uint32_t first_proof_index, uint8_t* proofs_out,
                          size_t proof_stride);
 
+/* Batched verifier, the counterpart of Proof::verify (taiga_halo2/src/proof.rs:45-54; plonk::verify_proof with
+ * SingleVerifier) for n_proofs proofs of one circuit: the transcript is replayed on the host, the final IPA check
+ * (one fixed-base MSM over the SRS + one ~100-term MSM per proof) runs on the device.  ok_out[i] = 1 iff proof i is
+ * accepted.  instance / instance_len as in tb_prove_batch. */
+tb_status tb_verify_batch(tb_ctx* ctx, const tb_pk* pk, uint32_t n_proofs, const uint8_t* instance, const uint32_t* instance_len,
+                          const uint8_t* proofs, size_t proof_stride, size_t proof_len, uint8_t* ok_out);
+
 #ifdef __cplusplus
 }
 #endif

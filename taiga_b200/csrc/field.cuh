@@ -99,6 +99,7 @@ struct alignas(16) Fe {
   uint32_t l[8];
 
   static TB_HD constexpr int params_id() { return P::id; }
+  static TB_HD constexpr uint32_t modulus_limb(int i) { return P::m(i); }
   static TB_HD Fe zero() { Fe z;
 #pragma unroll
     for (int i = 0; i < 8; ++i) z.l[i] = 0; return z; }

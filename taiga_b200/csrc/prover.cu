@@ -13,49 +13,9 @@
 #include <set>
 #include "capi_internal.cuh"
 #include "prover_kernels.cuh"
+#include "circuit.cuh"
 
 namespace tb {
-
-enum PolyKind { PK_INST = 0, PK_ADV, PK_PZ, PK_LZ, PK_LPIN, PK_LPTAB, PK_FIXED, PK_SIG, PK_H, PK_RANDOM };
-struct PolyId { int kind, idx; bool operator<(const PolyId& o) const { return kind != o.kind ? kind < o.kind : idx < o.idx; } bool operator==(const PolyId& o) const { return kind == o.kind && idx == o.idx; } };
-struct QueryRef { PolyId poly; int rot; };
-struct WsBlock { void* p = nullptr; size_t bytes = 0; };
-
-struct Circuit {
-  Ctx* ctx; const Srs* srs;
-  // deep copy of the description
-  uint32_t k, na, nf, ni, degree, bf, P, L, chunk, nsets, pieces; int ext_k, R; size_t n, usable;
-  std::vector<tb_query> aq, fq, iq; std::vector<tb_column> perm;
-  std::vector<tb_expr_node> nodes; std::vector<uint32_t> roots; std::vector<uint8_t> consts_bytes; uint32_t nconsts;
-  std::vector<std::vector<uint32_t>> lk_in, lk_tab; std::vector<tb_lookup> lk_desc;
-  Fp vk_repr;  // canonical
-  // device tables
-  Fp *fixed_vals = nullptr, *fixed_polys = nullptr, *fixed_cosets = nullptr, *sig_vals = nullptr, *sig_polys = nullptr, *sig_cosets = nullptr;
-  Fp *l0 = nullptr, *l_last = nullptr, *l_blind = nullptr, *consts = nullptr, *wr_inv = nullptr;
-  int2 *d_aq = nullptr, *d_fq = nullptr, *d_iq = nullptr, *d_perm = nullptr;
-  QProgram prog_gates, prog_lookups;
-  std::map<int, std::vector<QProgram>> gate_parts; std::map<int, std::vector<int>> gate_part_counts;   // keyed by number of parts
-  std::vector<Fp> t_inv; Fp delta, zeta, omega, r_inv;
-  Fp delta_c0[16];
-  // evaluation / multiopen structure (host)
-  std::vector<QueryRef> evals;            // transcript order of the evaluation section
-  std::vector<QueryRef> queries;          // multiopen query order
-  std::vector<int> rots;                  // distinct rotations (evaluation points), in order of first appearance in `queries`
-  std::vector<PolyId> uniq; std::vector<int> uniq_set; std::vector<std::vector<int>> point_sets;
-  uint32_t proof_len;
-  // persistent per-batch-size workspace and cached small tables (see prove_batch)
-  mutable std::map<int, std::vector<WsBlock>> ws;
-  mutable std::map<int, std::vector<void*>> cached_tables;
-
-  ~Circuit() {
-    for (auto& kv : ws) for (auto& b : kv.second) cudaFree(b.p);
-    for (auto& kv : cached_tables) for (void* p : kv.second) cudaFree(p);
-    for (void* p : {(void*)fixed_vals, (void*)fixed_polys, (void*)fixed_cosets, (void*)sig_vals, (void*)sig_polys, (void*)sig_cosets, (void*)l0, (void*)l_last,
-                    (void*)l_blind, (void*)consts, (void*)wr_inv, (void*)d_aq, (void*)d_fq, (void*)d_iq, (void*)d_perm, (void*)prog_gates.dev, (void*)prog_lookups.dev})
-      if (p) cudaFree(p);
-    for (auto& kv : gate_parts) for (auto& qp : kv.second) if (qp.dev) cudaFree(qp.dev);
-  }
-};
 
 template <class T> static T* dev_upload(const std::vector<T>& v) {
   T* p = nullptr;

@@ -55,6 +55,7 @@ _SIGS = {
     "tb_pk_proof_len": (_sz, [_vp]),
     "tb_pk_commitments": (_i, [_vp, _vp, _vp, _vp]),
     "tb_prove_batch": (_i, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _u32, _vp, _sz]),
+    "tb_verify_batch": (_i, [_vp, _vp, _u32, _vp, _vp, _vp, _sz, _sz, _vp]),
 }
 
 
@@ -255,6 +256,19 @@ class ProvingKey:
         ctx._check(ctx._lib.tb_prove_batch(ctx._h, self._h, B, _ptr(advice), _ptr(inst), _ptr(lens), _ptr(seed), first_proof_index,
                                            _ptr(out), self.proof_len))
         return [out[b].tobytes() for b in range(B)]
+
+    def verify_batch(self, instance, instance_len, proofs, ctx=None):
+        """Proof::verify for a batch: proofs = list of byte strings; returns a list of booleans."""
+        ctx = ctx or self.ctx
+        B = len(proofs)
+        plen = len(proofs[0])
+        assert all(len(p) == plen for p in proofs)
+        buf = np.frombuffer(b"".join(proofs), np.uint8).copy()
+        inst = _u8(instance)
+        lens = np.ascontiguousarray(instance_len, dtype=np.uint32)
+        ok = np.zeros(B, np.uint8)
+        ctx._check(ctx._lib.tb_verify_batch(ctx._h, self._h, B, _ptr(inst), _ptr(lens), _ptr(buf), plen, plen, _ptr(ok)))
+        return [bool(v) for v in ok]
 
     def close(self):
         if getattr(self, "_h", None):

@@ -63,3 +63,30 @@ def test_keygen_commitments_match_oracle(gpu_ctx, oracle_cpu):
     of, os_ = oracle_cpu.OracleKey(kd, srs).commitments()
     gf, gs = gsrs.load_circuit(kd).commitments()
     assert gf.tobytes() == of.tobytes() and gs.tobytes() == os_.tobytes()
+
+
+@pytest.mark.parametrize("k,wide,nl", [(6, False, 2), (7, True, 1), (6, False, 0)])
+def test_device_verifier_agrees_with_oracle(gpu_ctx, oracle_cpu, k, wide, nl):
+    """tb_verify_batch (product-side Proof::verify): accepts proofs made by the CUDA prover AND by the CPU oracle prover,
+    rejects tampered proofs, truncated proofs and wrong public inputs - same verdicts as the oracle's verifier."""
+    kd, make = cm.standard_plonk(k=k, wide=wide, n_lookups=nl)
+    srs, gsrs = small_srs(oracle_cpu, gpu_ctx, k)
+    okey = oracle_cpu.OracleKey(kd, srs)
+    pk = gsrs.load_circuit(kd)
+    wit = [kd.witness_arrays(make(200 + b)) for b in range(3)]
+    adv = np.stack([w[0] for w in wit]); inst = np.stack([w[1] for w in wit]); lens = wit[0][2]
+    proofs = pk.prove_batch(adv, inst, lens, bytes(range(32)))
+    proofs[2] = okey.prove(wit[2][0], wit[2][1], lens, bytes(32), proof_index=77)   # a CPU-made proof (different blinding)
+    assert pk.verify_batch(inst, lens, proofs) == [True, True, True]
+    bad = list(proofs)
+    t = bytearray(bad[0]); t[len(t) // 2] ^= 0x10; bad[0] = bytes(t)                   # flipped bit in an evaluation
+    t = bytearray(bad[1]); t[5] ^= 1; bad[1] = bytes(t)                                # flipped bit in the first commitment
+    verdict = pk.verify_batch(inst, lens, bad)
+    assert verdict == [False, False, True]
+    assert [okey.verify(wit[b][1], lens, bad[b]) == 0 for b in range(3)] == verdict
+    wrong_inst = inst.copy(); wrong_inst[1, 0] ^= 1
+    assert pk.verify_batch(wrong_inst, lens, proofs) == [True, False, True]
+    asg = make(200); asg.advice[2][0] = (asg.advice[2][0] + 1) % cm.P                  # unsatisfying witness -> rejected proof
+    adv2, _, _ = kd.witness_arrays(asg)
+    p2 = pk.prove_batch(adv2[None], wit[0][1][None], lens, bytes(32))
+    assert pk.verify_batch(wit[0][1][None], lens, p2) == [False]

@@ -35,3 +35,6 @@ def test_taiga_shape_proofs_bit_identical(gpu_ctx, gpu_srs, oracle_cpu, srs_fixt
     # tampering is rejected
     bad = bytearray(proofs[0]); bad[40] ^= 1
     assert okey.verify(wit[0][1], lens, bytes(bad)) != 0
+    # the product's own batched verifier gives the same verdicts
+    assert pk.verify_batch(inst, lens, proofs) == [True, True]
+    assert pk.verify_batch(inst, lens, [bytes(bad), ref]) == [False, True]
