@@ -321,14 +321,39 @@ struct alignas(16) Fe {
     return acc;
   }
   TB_HD Fe pow_u64(uint64_t e) const { uint32_t w[2] = {(uint32_t)e, (uint32_t)(e >> 32)}; return pow(w, 2); }
-  // Fermat inversion, 0 -> 0
+  // Inversion by the binary extended Euclidean algorithm (0 -> 0).  ~500 shift/subtract steps on 8 limbs (~15k
+  // instructions) instead of the ~380 dependent multiplies (~130k instructions) of a Fermat ladder: the single-thread
+  // latency of every normalisation to affine / challenge inversion drops ~5x.
   TB_HD Fe inv() const {
-    uint32_t e[8];
+    if (is_zero()) return zero();
+    uint32_t u[8], v[8], r[8], s[8];
+    { Fe x = from_mont();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) e[i] = P::m(i);
-    e[0] -= 2;  // m(0) == 1 -> borrow
-    e[0] = 0xffffffffu; e[1] = P::m(1) - 1;
-    return pow(e, 8);
+      for (int i = 0; i < 8; ++i) { u[i] = x.l[i]; v[i] = P::m(i); r[i] = 0; s[i] = 0; } }
+    r[0] = 1;
+    // invariants: r * x == u, s * x == v (mod m); u, v odd-reduced until one of them is 1
+    auto is_one = [](const uint32_t* a) { uint32_t o = a[0] ^ 1u; for (int i = 1; i < 8; ++i) o |= a[i]; return o == 0; };
+    auto shr1 = [](uint32_t* a, uint32_t top) { for (int i = 0; i < 7; ++i) a[i] = (a[i] >> 1) | (a[i + 1] << 31); a[7] = (a[7] >> 1) | (top << 31); };
+    auto half_mod = [&](uint32_t* a) {  // a <- a / 2 mod m
+      uint32_t carry = 0;
+      if (a[0] & 1u) { uint64_t c = 0; for (int i = 0; i < 8; ++i) { c += (uint64_t)a[i] + P::m(i); a[i] = (uint32_t)c; c >>= 32; } carry = (uint32_t)c; }
+      shr1(a, carry);
+    };
+    auto geq = [](const uint32_t* a, const uint32_t* b) { for (int i = 7; i >= 0; --i) { if (a[i] != b[i]) return a[i] > b[i]; } return true; };
+    auto sub = [](uint32_t* a, const uint32_t* b) { uint64_t br = 0; for (int i = 0; i < 8; ++i) { uint64_t d = (uint64_t)a[i] - b[i] - br; a[i] = (uint32_t)d; br = (d >> 32) & 1; } return (uint32_t)br; };
+    auto sub_mod = [&](uint32_t* a, const uint32_t* b) {  // a <- a - b mod m  (a, b < m)
+      if (sub(a, b)) { uint64_t c = 0; for (int i = 0; i < 8; ++i) { c += (uint64_t)a[i] + P::m(i); a[i] = (uint32_t)c; c >>= 32; } }
+    };
+    while (!is_one(u) && !is_one(v)) {
+      while (!(u[0] & 1u)) { shr1(u, 0); half_mod(r); }
+      while (!(v[0] & 1u)) { shr1(v, 0); half_mod(s); }
+      if (geq(u, v)) { sub(u, v); sub_mod(r, s); } else { sub(v, u); sub_mod(s, r); }
+    }
+    Fe out;
+    const uint32_t* res = is_one(u) ? r : s;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out.l[i] = res[i];
+    return out.to_mont();
   }
   // canonical-integer comparison of two canonical (non-Montgomery) values
   static TB_HD int cmp_raw(const Fe& a, const Fe& b) {

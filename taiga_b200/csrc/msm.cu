@@ -20,7 +20,6 @@ namespace tb {
 constexpr int MSM_CHUNK_MAX = 64;  // max entries accumulated by one thread (adaptive: chosen so the accumulation fills the GPU)
 constexpr int MSM_SEG = 8;         // buckets per thread in the running-sum reduction
 constexpr int MSM_FIXED_C = 13;    // fixed-base window: 4096 buckets per MSM, 20 table windows (measured best of 11/12/13/16 at k = 15)
-constexpr uint32_t MSM_SERIAL_UNITS = 4;    // buckets with <= 4 units are summed by one thread
 constexpr uint32_t MSM_HEAVY_UNITS = 1024;  // buckets with more units than this get a whole CTA (e.g. the top window of a variable-base MSM)
 
 int msm_default_window(int n, bool fixed_tables) {
@@ -141,17 +140,28 @@ __global__ void __launch_bounds__(256) msm_combine_kernel(const uint32_t* __rest
   if (lane == 0) buckets[b] = acc;
 }
 
-// same, one thread per bucket: cheaper when buckets have only a few units (large batches, chunk = 64)
+// 2^lpb_log lanes per bucket (1, 2, .. 32): every add a warp issues costs the same whether 1 or 32 of its lanes are live, so a
+// full warp per bucket spends as many issue slots on the tree as the accumulation itself when buckets hold ~10 units.  The
+// host picks the narrowest group that still leaves a few warps per SM sub-partition; buckets with more than 4 * lanes units are
+// left to the warp / heavy kernels.
 template <class B>
-__global__ void __launch_bounds__(128) msm_combine_serial_kernel(const uint32_t* __restrict__ unit_off, const Xyzz<B>* __restrict__ partial, uint32_t nb_total,
-                                                                  Xyzz<B>* __restrict__ buckets) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb_total) return;
-  uint32_t u0 = unit_off[b], u1 = unit_off[b + 1];
-  if (u1 - u0 > MSM_SERIAL_UNITS) return;  // handled by the warp / heavy kernels
+__global__ void __launch_bounds__(128) msm_combine_sub_kernel(const uint32_t* __restrict__ unit_off, const Xyzz<B>* __restrict__ partial, uint32_t nb_total,
+                                                               uint32_t lpb_log, Xyzz<B>* __restrict__ buckets) {
+  const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x, lpb = 1u << lpb_log;
+  const uint32_t b = gt >> lpb_log, l = gt & (lpb - 1);
+  uint32_t u0 = 0, u1 = 0;
+  if (b < nb_total) { u0 = unit_off[b]; u1 = unit_off[b + 1]; }
+  const bool mine = b < nb_total && (u1 - u0) <= (4u << lpb_log);
   Xyzz<B> acc = Xyzz<B>::inf();
-  for (uint32_t u = u0; u < u1; ++u) acc.add(partial[u]);
-  buckets[b] = acc;
+  if (mine) for (uint32_t u = u0 + l; u < u1; u += lpb) acc.add(partial[u]);
+  for (uint32_t d = lpb >> 1; d >= 1; d >>= 1) {
+    Xyzz<B> o;
+    { const uint32_t* src = reinterpret_cast<const uint32_t*>(&acc); uint32_t* dst = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) dst[i] = __shfl_down_sync(0xffffffffu, src[i], d, lpb); }
+    if (l < d) acc.add(o);
+  }
+  if (mine && l == 0) buckets[b] = acc;
 }
 
 // one CTA per oversized bucket (grid-stride over the heavy list)
@@ -291,13 +301,17 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
                                                                           nb_total, 1u << chunk_log, entries.get(), partial.get());
   TB_LAUNCH_CHECK();
   ps.reset(); ps.reset(new ProfScope(ctx, PC_MSM_REDUCE));
-  // three disjoint classes of buckets: <= 4 units (one thread), <= 1024 units (one warp), more (one CTA each).
-  // Small problems (latency matters, lanes are free) let the warp kernel take the first class too: one launch less.
-  const bool warp_only = nb_total64 <= (64u << 10);
-  if (!warp_only) msm_combine_serial_kernel<B><<<(nb_total + 127) / 128, 128, 0, st>>>(unit_off.get(), partial.get(), nb_total, buckets.get());
-  if (warp_only || (max_entries >> chunk_log) > MSM_SERIAL_UNITS)
-    msm_combine_kernel<B><<<(unsigned)(((uint64_t)nb_total * 32 + 255) / 256), 256, 0, st>>>(unit_off.get(), partial.get(), nb_total,
-                                                                                              warp_only ? 0u : MSM_SERIAL_UNITS, buckets.get());
+  // three disjoint classes of buckets: <= 4 * lanes units (a group of `lanes` threads), <= 1024 units (one warp), more (one
+  // CTA each).  lanes: as wide as keeps ~4 warps per SM sub-partition busy, no wider than the average bucket needs.
+  uint32_t lpb_log = 0;
+  { const uint64_t avg_units = ((max_entries >> chunk_log) + nb_total64 - 1) / nb_total64;
+    const uint64_t warps_target = 16ull * (uint64_t)ctx->sm_count;
+    while (lpb_log < 5 && ((nb_total64 << (lpb_log + 1)) >> 5) <= warps_target && (1ull << lpb_log) < avg_units) ++lpb_log; }
+  const uint32_t sub_units = 4u << lpb_log;
+  msm_combine_sub_kernel<B><<<(unsigned)((((uint64_t)nb_total << lpb_log) + 127) / 128), 128, 0, st>>>(unit_off.get(), partial.get(), nb_total, lpb_log,
+                                                                                                      buckets.get());
+  if ((max_entries >> chunk_log) > sub_units)
+    msm_combine_kernel<B><<<(unsigned)(((uint64_t)nb_total * 32 + 255) / 256), 256, 0, st>>>(unit_off.get(), partial.get(), nb_total, sub_units, buckets.get());
   if ((max_entries >> chunk_log) > MSM_HEAVY_UNITS)  // e.g. the top window of a variable-base MSM, or a witness column that is mostly ones
     msm_combine_heavy_kernel<B><<<(unsigned)(max_heavy < 296 ? max_heavy : 296), 256, 0, st>>>(heavy.get(), n_heavy.get(), unit_off.get(), partial.get(), buckets.get());
   TB_LAUNCH_CHECK();
