@@ -50,18 +50,80 @@ struct FqParams {  // Vesta base field = Pallas scalar field
 #endif
 #if defined(__CUDA_ARCH__) && !defined(TB_PORTABLE_FIELD)
 #define TB_PTX_FIELD 1
-// One row of the operand-scanning Montgomery product: t[0..8] += a[0..7] * bi.
-// The eight 32x32+32 -> 64-bit products are independent IMAD.WIDE.U32 (no carries); their high words are folded into
-// the next limb with a single add-with-carry chain.  (sm_100 has no IMAD with carry-out: `madc.lo.cc` costs an extra
-// IADD3.X per product, so the carries are kept off the multiplier.)  Requires t[8] == 0 on entry.
-__device__ __forceinline__ void tb_mul_row(uint32_t* t, const uint32_t* a, uint32_t bi) {
-  uint32_t lo[8], hi[8];
+// Montgomery product on the FMA pipe.  sm_100 issues IMAD on the fma pipe and IADD3 on the alu pipe, each at one warp
+// instruction per two cycles per sub-partition; a product whose carries are resolved with add-with-carry chains is
+// alu-bound at ~2x its IMAD count (ncu: alu 57 % / fma 29 % in the NTT).  Here the running sum T is kept as two
+// interleaved accumulators, T = X + Y * 2^32: the products a[2k] * bi land on the 64-bit slots of X and a[2k+1] * bi on
+// those of Y, so `mad.lo.cc / madc.hi.cc` pairs fuse into IMAD.WIDE.U32(.X) with the carry travelling in a predicate
+// -- no alu instruction per product.  Dividing by 2^32 after a reduction row swaps the roles: X' = Y, Y' = X >> 64, and
+// the odd limb X[1] is added at the bottom of X'.  (Restated from the published even/odd CIOS technique used by GPU
+// big-number libraries; verified against big-integer arithmetic in scratch simulation and tests/test_host_arith.py +
+// the GPU field tests.)  Each asm block is self-contained with respect to the carry flag.
+//
+// first row: X = a_even * b0, Y = a_odd * b0
+__device__ __forceinline__ void tb_eo_first(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint64_t p = (uint64_t)a[j] * bi + t[j];
-    lo[j] = (uint32_t)p; hi[j] = (uint32_t)(p >> 32);
+  for (int k = 0; k < 4; ++k) {
+    uint64_t p = (uint64_t)a[2 * k] * bi, q = (uint64_t)a[2 * k + 1] * bi;
+    X[2 * k] = (uint32_t)p; X[2 * k + 1] = (uint32_t)(p >> 32);
+    Y[2 * k] = (uint32_t)q; Y[2 * k + 1] = (uint32_t)(q >> 32);
   }
-  t[0] = lo[0];
+}
+// row i > 0.  In: X (old even accumulator, X[0] == 0 after its reduction), Y (old odd).  Out: X' = Y + X[1] + a_even * bi
+// (returned in Y's registers), Y' = (X >> 64) + a_odd * bi (+ carries) returned in N.
+__device__ __forceinline__ void tb_eo_row(uint32_t* Y /* in: old Y, out: new X */, uint32_t* N /* out: new Y */, const uint32_t* X /* old X */,
+                                          const uint32_t* a, uint32_t bi) {
+  asm("add.cc.u32 %0, %0, %9;\n\t"
+      "madc.lo.cc.u32 %1, %16, %20, %10;\n\t"
+      "madc.hi.cc.u32 %2, %16, %20, %11;\n\t"
+      "madc.lo.cc.u32 %3, %17, %20, %12;\n\t"
+      "madc.hi.cc.u32 %4, %17, %20, %13;\n\t"
+      "madc.lo.cc.u32 %5, %18, %20, %14;\n\t"
+      "madc.hi.cc.u32 %6, %18, %20, %15;\n\t"
+      "madc.lo.cc.u32 %7, %19, %20, 0;\n\t"
+      "madc.hi.u32 %8, %19, %20, 0;"
+      : "+r"(Y[0]), "=&r"(N[0]), "=&r"(N[1]), "=&r"(N[2]), "=&r"(N[3]), "=&r"(N[4]), "=&r"(N[5]), "=&r"(N[6]), "=&r"(N[7])
+      : "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]), "r"(X[6]), "r"(X[7]), "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(bi));
+  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7]), "+r"(N[7])
+      : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(bi));
+}
+// Pasta reduction row: mi = -X[0] (since -m^-1 = -1 mod 2^32); T += mi * m with m = 1 + m1 2^32 + m2 2^64 + m3 2^96 + m7 2^224.
+// Odd limbs (m1, m3, 0, m7) go to Y, even limbs (1, m2, 0, 0) to X; afterwards X[0] == 0.
+__device__ __forceinline__ void tb_eo_red(uint32_t* X, uint32_t* Y, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t m7) {
+  const uint32_t mi = 0u - X[0];
+  asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\t"
+      "madc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+      "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+      "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+      "addc.cc.u32 %4, %4, 0;\n\t"
+      "addc.cc.u32 %5, %5, 0;\n\t"
+      "madc.lo.cc.u32 %6, %8, %11, %6;\n\t"
+      "madc.hi.u32 %7, %8, %11, %7;"
+      : "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7])
+      : "r"(mi), "r"(m1), "r"(m3), "r"(m7));
+  asm("add.cc.u32 %0, %0, %9;\n\t"
+      "addc.cc.u32 %1, %1, 0;\n\t"
+      "madc.lo.cc.u32 %2, %9, %10, %2;\n\t"
+      "madc.hi.cc.u32 %3, %9, %10, %3;\n\t"
+      "addc.cc.u32 %4, %4, 0;\n\t"
+      "addc.cc.u32 %5, %5, 0;\n\t"
+      "addc.cc.u32 %6, %6, 0;\n\t"
+      "addc.cc.u32 %7, %7, 0;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(Y[7])
+      : "r"(mi), "r"(m2));
+}
+// result = Y + (X >> 32)   (< 2m)
+__device__ __forceinline__ void tb_eo_merge(uint32_t* r, const uint32_t* X, const uint32_t* Y) {
   asm("add.cc.u32 %0, %8, %16;\n\t"
       "addc.cc.u32 %1, %9, %17;\n\t"
       "addc.cc.u32 %2, %10, %18;\n\t"
@@ -70,27 +132,9 @@ __device__ __forceinline__ void tb_mul_row(uint32_t* t, const uint32_t* a, uint3
       "addc.cc.u32 %5, %13, %21;\n\t"
       "addc.cc.u32 %6, %14, %22;\n\t"
       "addc.u32 %7, %15, 0;"
-      : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8])
-      : "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]), "r"(hi[7]),
-        "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]));
-}
-// Pasta-specific reduction row: q = -t0 (since -m^-1 = -1 mod 2^32), t += q * m with m = 1 + m1 2^32 + m2 2^64 + m3 2^96 + 2^30 2^224;
-// afterwards t[0] == 0 and the caller shifts the window down by one limb.
-__device__ __forceinline__ void tb_red_row(uint32_t* t, uint32_t m1, uint32_t m2, uint32_t m3) {
-  const uint32_t q = 0u - t[0], ql = q << 30, qh = q >> 2;
-  const uint64_t r1 = (uint64_t)q * m1 + t[1], r2 = (uint64_t)q * m2 + t[2], r3 = (uint64_t)q * m3 + t[3];
-  asm("add.cc.u32 %0, %0, %9;\n\t"         // t0 + q = 0 (mod 2^32), carry = (t0 != 0)
-      "addc.cc.u32 %1, %10, 0;\n\t"
-      "addc.cc.u32 %2, %11, %13;\n\t"
-      "addc.cc.u32 %3, %12, %14;\n\t"
-      "addc.cc.u32 %4, %4, %15;\n\t"
-      "addc.cc.u32 %5, %5, 0;\n\t"
-      "addc.cc.u32 %6, %6, 0;\n\t"
-      "addc.cc.u32 %7, %7, %16;\n\t"
-      "addc.u32 %8, %8, %17;"
-      : "+r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
-      : "r"(q), "r"((uint32_t)r1), "r"((uint32_t)r2), "r"((uint32_t)r3), "r"((uint32_t)(r1 >> 32)), "r"((uint32_t)(r2 >> 32)), "r"((uint32_t)(r3 >> 32)),
-        "r"(ql), "r"(qh));
+      : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
+      : "r"(Y[0]), "r"(Y[1]), "r"(Y[2]), "r"(Y[3]), "r"(Y[4]), "r"(Y[5]), "r"(Y[6]), "r"(Y[7]),
+        "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]), "r"(X[6]), "r"(X[7]));
 }
 #endif
 
@@ -221,22 +265,25 @@ struct alignas(16) Fe {
   // the (latency-bound) EC formulas, whose multiplies come in independent pairs.
   struct Pair { Fe a, b; };
   static __device__ __noinline__ Pair mul2_call(Fe a, Fe b, Fe c, Fe d) {
-    uint32_t t[9], u[9];
+    static_assert(P::m(0) == 1 && P::m(4) == 0 && P::m(5) == 0 && P::m(6) == 0, "Pasta-shaped modulus expected");
+    uint32_t X[8], Y[8], U[8], V[8];
+    tb_eo_first(X, Y, a.l, b.l[0]);
+    tb_eo_first(U, V, c.l, d.l[0]);
+    tb_eo_red(X, Y, P::m(1), P::m(2), P::m(3), P::m(7));
+    tb_eo_red(U, V, P::m(1), P::m(2), P::m(3), P::m(7));
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { t[i] = 0; u[i] = 0; }
+    for (int i = 1; i < 8; ++i) {
+      uint32_t N[8], W[8];
+      tb_eo_row(Y, N, X, a.l, b.l[i]);
+      tb_eo_row(V, W, U, c.l, d.l[i]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      tb_mul_row(t, a.l, b.l[i]);
-      tb_mul_row(u, c.l, d.l[i]);
-      tb_red_row(t, P::m(1), P::m(2), P::m(3));
-      tb_red_row(u, P::m(1), P::m(2), P::m(3));
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { t[j] = t[j + 1]; u[j] = u[j + 1]; }
-      t[8] = 0; u[8] = 0;
+      for (int j = 0; j < 8; ++j) { X[j] = Y[j]; Y[j] = N[j]; U[j] = V[j]; V[j] = W[j]; }
+      tb_eo_red(X, Y, P::m(1), P::m(2), P::m(3), P::m(7));
+      tb_eo_red(U, V, P::m(1), P::m(2), P::m(3), P::m(7));
     }
     Pair r;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { r.a.l[i] = t[i]; r.b.l[i] = u[i]; }
+    tb_eo_merge(r.a.l, X, Y);
+    tb_eo_merge(r.b.l, U, V);
     cond_sub(r.a.l); cond_sub(r.b.l);
     return r;
   }
@@ -258,21 +305,21 @@ struct alignas(16) Fe {
   }
   static TB_HD Fe mul_body(const Fe& a, const Fe& b) {
 #ifdef TB_PTX_FIELD
-    // requires a < m (any 256-bit b): invariant t < 2m after every row, so 9 limbs never overflow
-    uint32_t t[9];
+    // requires a < m (any 256-bit b): invariant T < 2m after every row
+    static_assert(P::m(0) == 1 && P::m(4) == 0 && P::m(5) == 0 && P::m(6) == 0, "Pasta-shaped modulus expected");
+    uint32_t X[8], Y[8];
+    tb_eo_first(X, Y, a.l, b.l[0]);
+    tb_eo_red(X, Y, P::m(1), P::m(2), P::m(3), P::m(7));
 #pragma unroll
-    for (int i = 0; i < 9; ++i) t[i] = 0;
+    for (int i = 1; i < 8; ++i) {
+      uint32_t N[8];
+      tb_eo_row(Y, N, X, a.l, b.l[i]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      tb_mul_row(t, a.l, b.l[i]);
-      tb_red_row(t, P::m(1), P::m(2), P::m(3));
-#pragma unroll
-      for (int j = 0; j < 8; ++j) t[j] = t[j + 1];
-      t[8] = 0;
+      for (int j = 0; j < 8; ++j) { X[j] = Y[j]; Y[j] = N[j]; }
+      tb_eo_red(X, Y, P::m(1), P::m(2), P::m(3), P::m(7));
     }
     Fe r;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r.l[i] = t[i];
+    tb_eo_merge(r.l, X, Y);
     cond_sub(r.l);
     return r;
 #else
