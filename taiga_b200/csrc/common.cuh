@@ -1,5 +1,6 @@
 // Shared host-side plumbing for libtaiga_b200: context, error handling, stream-ordered device memory.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -37,6 +38,9 @@ template <class F> struct FieldTables {
 enum ProfCat { PC_NTT = 0, PC_MSM_SORT, PC_MSM_ACCUM, PC_MSM_REDUCE, PC_QUOT_GATES, PC_QUOT_FINISH, PC_IPA_FOLD, PC_TRANSCRIPT, PC_LOOKUP_SORT,
                PC_POLY, PC_COUNT };
 struct ProfRec { int cat; cudaEvent_t a, b; };
+
+// experiment knob: integer from the environment (read on every call; only used on host set-up paths)
+inline int tb_tune(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 
 struct Ctx {
   int device = 0;

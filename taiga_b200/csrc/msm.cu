@@ -231,6 +231,71 @@ __global__ void __launch_bounds__(256) msm_bucket_reduce_kernel(const Xyzz<B>* _
   }
 }
 
+// ---- weighted bucket sum for one window set, two-level: b = hi * S + lo (S = 2^s_log columns, H = NB / S rows)
+//   sum_b (b+1) B_b = sum_lo (lo+1) C_lo + S * sum_hi hi * R_hi,   C_lo = sum_hi B[hi][lo],  R_hi = sum_lo B[hi][lo]
+// and sum_j (j+1) C_j = sum_j Suffix_j(C), sum_j j R_j = sum_{j>=1} Suffix_j(R).  Every step is a tree: the dependent chain is
+// ~27 point additions (line sums 8, suffix scan 6, tree 6, 6 doublings, 1) against ~46 for running sums + a 12-bit scalar
+// multiple per thread + a block tree -- these kernels are pure latency (one launch per commitment / IPA round).
+//
+// kernel 1: the S column sums and H row sums of every group, 16 lanes per line
+template <class B>
+__global__ void __launch_bounds__(128) msm_linesum_kernel(const Xyzz<B>* __restrict__ buckets, int NB, int s_log, uint32_t groups,
+                                                           Xyzz<B>* __restrict__ lines) {
+  const int S = 1 << s_log, H = NB >> s_log, nl = S + H;
+  const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x, line = gt >> 4, l = gt & 15;
+  const bool live = line < groups * (uint32_t)nl;
+  Xyzz<B> acc = Xyzz<B>::inf();
+  if (live) {
+    const uint32_t g = line / nl, L = line % nl;
+    const Xyzz<B>* bk = buckets + (size_t)g * NB;
+    if ((int)L < S) { for (int hi = l; hi < H; hi += 16) acc.add(bk[(size_t)hi * S + L]); }
+    else { const Xyzz<B>* row = bk + (size_t)(L - S) * S; for (int lo = l; lo < S; lo += 16) acc.add(row[lo]); }
+  }
+  for (int d = 8; d >= 1; d >>= 1) {
+    Xyzz<B> o;
+    { const uint32_t* src = reinterpret_cast<const uint32_t*>(&acc); uint32_t* dst = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) dst[i] = __shfl_down_sync(0xffffffffu, src[i], d, 16); }
+    if ((int)l < d) acc.add(o);
+  }
+  if (live && l == 0) lines[line] = acc;
+}
+// kernel 2: one CTA per group, blockDim = 2 * max(S, H): suffix scans of the two line vectors, their totals, the final
+// combination and (optionally) the normalisation to affine
+template <class B>
+__global__ void __launch_bounds__(256) msm_weighted_kernel(const Xyzz<B>* __restrict__ lines, int s_log, int h_log, Xyzz<B>* __restrict__ out, Aff<B>* __restrict__ aff_out) {
+  extern __shared__ uint4 mw_smem[];
+  Xyzz<B>* sm = reinterpret_cast<Xyzz<B>*>(mw_smem);
+  const int S = 1 << s_log, H = 1 << h_log, half = blockDim.x >> 1;
+  const int part = threadIdx.x >= (unsigned)half, j = threadIdx.x - part * half, len = part ? H : S;
+  const Xyzz<B>* src = lines + (size_t)blockIdx.x * (S + H) + (part ? S : 0);
+  Xyzz<B>* v = sm + part * half;
+  Xyzz<B> acc = j < len ? src[j] : Xyzz<B>::inf();
+  v[j] = acc;
+  __syncthreads();
+  for (int d = 1; d < half; d <<= 1) {   // suffix scan (Hillis-Steele)
+    const bool act = j + d < len;
+    Xyzz<B> o;
+    if (act) o = v[j + d];
+    __syncthreads();
+    if (act) { acc.add(o); v[j] = acc; }
+    __syncthreads();
+  }
+  if (part && j == 0) v[0] = Xyzz<B>::inf();   // rows are weighted hi, not hi + 1
+  __syncthreads();
+  for (int d = half >> 1; d >= 1; d >>= 1) {   // totals of the suffixes
+    if (j < d) { Xyzz<B> a = v[j]; a.add(v[j + d]); v[j] = a; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    Xyzz<B> r = sm[half];
+    for (int i = 0; i < s_log; ++i) r = r.dbl();
+    r.add(sm[0]);
+    out[blockIdx.x] = r;
+    if (aff_out) aff_out[blockIdx.x] = r.to_affine();
+  }
+}
+
 template <class B>
 __global__ void __launch_bounds__(256) msm_window_kernel(const Xyzz<B>* __restrict__ seg_out, int nt, Xyzz<B>* __restrict__ win_out) {
   __shared__ Xyzz<B> sm[8];
@@ -286,7 +351,7 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
 
   // adaptive chunk: aim at ~4 waves of 512 threads per SM so that small batches still fill the machine
   uint32_t chunk_log = 3;
-  { const uint64_t target_units = 4ull * 512 * (uint64_t)ctx->sm_count;
+  { const uint64_t target_units = (uint64_t)tb_tune("TB_MSM_UNITS_PER_SM", 2048) * (uint64_t)ctx->sm_count;
     while ((1u << chunk_log) < (uint32_t)MSM_CHUNK_MAX && (max_entries >> chunk_log) > target_units) ++chunk_log; }
   const uint64_t max_units = nb_total64 + (max_entries >> chunk_log) + 1;
   const uint64_t max_heavy = (max_entries >> chunk_log) / MSM_HEAVY_UNITS + 1;
@@ -305,7 +370,7 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
   // CTA each).  lanes: as wide as keeps ~4 warps per SM sub-partition busy, no wider than the average bucket needs.
   uint32_t lpb_log = 0;
   { const uint64_t avg_units = ((max_entries >> chunk_log) + nb_total64 - 1) / nb_total64;
-    const uint64_t warps_target = 16ull * (uint64_t)ctx->sm_count;
+    const uint64_t warps_target = (uint64_t)tb_tune("TB_MSM_SUB_WARPS_PER_SM", 16) * (uint64_t)ctx->sm_count;
     while (lpb_log < 5 && ((nb_total64 << (lpb_log + 1)) >> 5) <= warps_target && (1ull << lpb_log) < avg_units) ++lpb_log; }
   const uint32_t sub_units = 4u << lpb_log;
   msm_combine_sub_kernel<B><<<(unsigned)((((uint64_t)nb_total << lpb_log) + 127) / 128), 128, 0, st>>>(unit_off.get(), partial.get(), nb_total, lpb_log,
@@ -316,30 +381,43 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
     msm_combine_heavy_kernel<B><<<(unsigned)(max_heavy < 296 ? max_heavy : 296), 256, 0, st>>>(heavy.get(), n_heavy.get(), unit_off.get(), partial.get(), buckets.get());
   TB_LAUNCH_CHECK();
 
-  const int seg = NB < MSM_SEG ? NB : MSM_SEG;
+  const int seg_t = tb_tune("TB_MSM_SEG", MSM_SEG);
+  const int seg = NB < seg_t ? NB : seg_t;
   const int nt = NB / seg;
   const uint32_t groups = (uint32_t)K * wsep;
-  if (wsep == 1 && nt <= 256) {
+  Aff<B>* const aff_out = reinterpret_cast<Aff<B>*>(cfg_in.affine_out);
+  if (wsep == 1 && NB < 64) {
     int threads = ((nt + 31) / 32) * 32;
-    msm_bucket_reduce_kernel<B><<<groups, threads, 0, st>>>(buckets.get(), NB, seg, nt, out, reinterpret_cast<Aff<B>*>(cfg_in.affine_out));
+    msm_bucket_reduce_kernel<B><<<groups, threads, 0, st>>>(buckets.get(), NB, seg, nt, out, aff_out);
     TB_LAUNCH_CHECK();
     ctx->launches += 6;
+    return;
+  }
+  if (wsep == 1) {
+    const int lb = c - 1, s_log = (lb + 1) / 2, h_log = lb - s_log;
+    const int nl = (1 << s_log) + (1 << h_log), threads = 2 << s_log;
+    TB_REQUIRE(threads <= 256, "fixed-base window too wide for the weighted-sum kernel (c <= 15)");
+    DevBuf<Xyzz<B>> lines(ctx, (size_t)groups * nl);
+    msm_linesum_kernel<B><<<(unsigned)(((uint64_t)groups * nl * 16 + 127) / 128), 128, 0, st>>>(buckets.get(), NB, s_log, groups, lines.get());
+    TB_LAUNCH_CHECK();
+    const size_t smem = (size_t)threads * sizeof(Xyzz<B>);
+    if (smem > 48 * 1024) {
+      static bool attr[2] = {false, false};
+      if (!attr[B::params_id()]) { TB_CUDA(cudaFuncSetAttribute(msm_weighted_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024)); attr[B::params_id()] = true; }
+    }
+    msm_weighted_kernel<B><<<groups, threads, smem, st>>>(lines.get(), s_log, h_log, out, aff_out);
+    TB_LAUNCH_CHECK();
+    ctx->launches += 7;
     return;
   }
   DevBuf<Xyzz<B>> seg_out(ctx, (size_t)groups * nt), win(ctx, groups);
   msm_segsum_kernel<B><<<(groups * nt + 127) / 128, 128, 0, st>>>(buckets.get(), NB, seg, nt, groups, seg_out.get());
   TB_LAUNCH_CHECK();
-  if (wsep == 1) {
-    msm_window_kernel<B><<<groups, 256, 0, st>>>(seg_out.get(), nt, out);
-    TB_LAUNCH_CHECK();
-    ctx->launches += 7;
-  } else {
-    msm_window_kernel<B><<<groups, 256, 0, st>>>(seg_out.get(), nt, win.get());
-    TB_LAUNCH_CHECK();
-    msm_horner_kernel<B><<<(K + 31) / 32, 32, 0, st>>>(win.get(), wsep, c, K, out);
-    TB_LAUNCH_CHECK();
-    ctx->launches += 8;
-  }
+  msm_window_kernel<B><<<groups, 256, 0, st>>>(seg_out.get(), nt, win.get());
+  TB_LAUNCH_CHECK();
+  msm_horner_kernel<B><<<(K + 31) / 32, 32, 0, st>>>(win.get(), wsep, c, K, out);
+  TB_LAUNCH_CHECK();
+  ctx->launches += 8;
 }
 
 template void msm_run<Fq, Fp>(Ctx*, const Fp*, long long, const Aff<Fq>*, long long, int, int, const MsmConfig&, Xyzz<Fq>*);

@@ -118,7 +118,7 @@ static Circuit* circuit_load(Ctx* ctx, const Srs* srs, const tb_cs_desc* cs, con
   // expression programs (descriptor rebuilt from the deep copy so pointers stay valid)
   { tb_cs_desc d = *cs;
     q_compile_gates(&d, &C.prog_gates);
-    for (int parts : {1, 2, 4, 8}) q_compile_gates_split(&d, parts, &C.gate_parts[parts], &C.gate_part_counts[parts]);
+    for (int parts : {1, 2, 4, 8, 16}) q_compile_gates_split(&d, parts, &C.gate_parts[parts], &C.gate_part_counts[parts]);
     if (getenv("TB_DEBUG")) {
       fprintf(stderr, "[tb] circuit k=%u degree=%u: gates program %d instr / %d regs; lookups %d instr / %d regs\n", C.k, C.degree, C.prog_gates.ninstr,
               C.prog_gates.nregs, C.prog_lookups.ninstr, C.prog_lookups.nregs);
@@ -431,7 +431,7 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   // Constraint-parallel split of the gate program.  More parts = shorter per-thread chains (latency at small batches) AND
   // fewer live temporaries per part = smaller shared-memory register file = higher occupancy (ncu: 6 warps/SM with one
   // 26-register program vs 20 warps/SM with eight <=11-register parts), for ~15% more instructions in total.
-  int gparts = Q_MAX_PARTS;
+  int gparts = tb_tune("TB_Q_PARTS", 8);
   while (gparts > 1 && C.gate_parts.at(gparts).size() < (size_t)gparts) gparts /= 2;
   const std::vector<QProgram>& gprogs = C.gate_parts.at(gparts); const std::vector<int>& gcounts = C.gate_part_counts.at(gparts);
   { Prog p; for (size_t i = 1; i < gprogs.size(); ++i) p.op(S_POWI, V_YPOW + (int)i, V_Y, 0, (uint32_t)gcounts[i]); run_prog(p); }
@@ -592,7 +592,6 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
     ipa_extras_kernel<<<(B + 31) / 32, 32, 0, st>>>(ex.get(), vars.get(), NV, V_LR, V_RR, V_VL, V_VR, V_Z, B);
     // L_j, R_j = <cL | cR, g> + l_rand * w + (value * z) * u : one batched fixed-base MSM, K = 2 per proof
     srs.commit_xyzz(ctx, false, cLR.get(), nn, 2 * B, ex.get(), 2, accLR.get(), ptLR.get());
-    if (((1 << (srs.c - 1)) / 8) > 256) points_to_affine<Fq>(ctx, accLR.get(), 2 * B, ptLR.get());
     tr.points(ptLR.get(), 2, 2, true);
     tr.squeeze(VP(V_U), NV, 1);
     scalar_program(ctx, vars.get(), NV, d_round, (int)round_prog.ins.size(), dconsts, B);

@@ -26,7 +26,7 @@ struct QProgram {           // compiled once per circuit (host), resident on the
 void q_compile_gates(const tb_cs_desc* cs, QProgram* out);
 // the constraint list split into `parts` contiguous groups of similar cost, one program each (row-parallel AND
 // constraint-parallel evaluation for small batches); counts[p] = number of constraints folded by part p
-constexpr int Q_MAX_PARTS = 8;
+constexpr int Q_MAX_PARTS = 16;
 void q_compile_gates_split(const tb_cs_desc* cs, int parts, std::vector<QProgram>* out, std::vector<int>* counts);
 struct QPartList { const QInstr* prog[Q_MAX_PARTS]; int ninstr[Q_MAX_PARTS]; int nparts; long long part_stride; };
 void q_compile_lookups(const tb_cs_desc* cs, QProgram* out);

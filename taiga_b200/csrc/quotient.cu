@@ -207,7 +207,8 @@ static void q_launch(Ctx* c, const QPartList& pl, int nregs, const QData& d, int
   static bool attr = false;
   if (!attr) { TB_CUDA(cudaFuncSetAttribute(q_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
   int T = (96 * 1024) / (nregs * 32);
-  T = T >= 128 ? 128 : (T / 32) * 32;
+  const int tmax = tb_tune("TB_Q_THREADS", 128);
+  T = T >= tmax ? tmax : (T / 32) * 32;
   TB_REQUIRE(T >= 32, "constraint program register file does not fit shared memory");
   if (d.n < T) T = d.n < 32 ? 32 : d.n;
   size_t smem = (size_t)nregs * T * 32;

@@ -23,7 +23,7 @@ struct Srs {
     Srs* s = new Srs();
     s->ctx = ctx; s->k = k; s->n = size_t(1) << k;
     int c = (int)k - 2; if (c < 4) c = 4; if (c > 13) c = 13;  // 13: 4096 buckets per MSM at k = 15 (see msm.cu MSM_FIXED_C)
-    if (const char* e = getenv("TB_FIXED_C")) { int v = atoi(e); if (v >= 4 && v <= 16) c = v; }  // tuning knob for experiments
+    if (const char* e = getenv("TB_FIXED_C")) { int v = atoi(e); if (v >= 4 && v <= 15) c = v; }  // tuning knob for experiments
     s->c = c; s->W = (256 + c - 1) / c;
     size_t n = s->n;
     try {
@@ -67,7 +67,6 @@ struct Srs {
   void commit(Ctx* c_, bool lagrange, const Fp* scalars, long long stride, int K, const Fp* blinds, Aff<Fq>* out) const {
     DevBuf<Xyzz<Fq>> acc(c_, K);
     commit_xyzz(c_, lagrange, scalars, stride, K, blinds, 1, acc.get(), out);
-    if (((1 << (c - 1)) / 8) > 256) points_to_affine<Fq>(c_, acc.get(), K, out);  // only when the fused reduction was not used
   }
 };
 
