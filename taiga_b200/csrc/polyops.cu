@@ -3,6 +3,7 @@
 // Replaces halo2_proofs `arithmetic::{eval_polynomial, kate_division, compute_inner_product}`, `BatchInvert` and the
 // `Polynomial` +, * operators used by plonk::create_proof / multiopen / commitment (EXT).
 #define TB_NOINLINE_MUL 0  // loop-structured kernels: small code, keep the multiply inline
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "prover.cuh"
 
@@ -137,54 +138,80 @@ void powers(Ctx* c, Fp* out, long long out_stride, const Fp* x, long long x_stri
 }
 
 // ---------------------------------------------------------------- Kate division (suffix linear recurrence q_j = a_{j+1} + z q_{j+1})
-constexpr int KD_THREADS = 512;
+// One thread-block CLUSTER per polynomial: 8 CTAs x 512 threads cover n = 2^15 coefficients with 8 per thread, so the
+// dependent chain is 8 (local Horner) + 9 (block suffix composition) + <= 7 (cluster composition over distributed shared
+// memory) + 8 (replay with the incoming carry) multiply-adds, spread over 8 SMs -- it used to be 64 + 9 + 64 on one SM.
+// The kernel is pure latency (one polynomial per proof per opening point).  Polynomials shorter than 4096 use a single CTA.
+constexpr int KD_THREADS = 512, KD_CLUSTER = 8, KD_MAX_M = 8;
 __global__ void __launch_bounds__(KD_THREADS) kate_div_kernel(Fp* out, long long out_stride, const Fp* in, long long in_stride, const Fp* zs,
-                                                               long long z_stride, int n) {
-  extern __shared__ uint4 kd_smem[];
+                                                               long long z_stride, int n, int cs /* CTAs per polynomial */) {
+  namespace cg = cooperative_groups;
+  __shared__ uint4 kd_smem[(2 * KD_THREADS + 3) * 2];
   Fp* A = reinterpret_cast<Fp*>(kd_smem);       // additive part of the suffix map
   Fp* M = A + KD_THREADS;                        // multiplicative part
-  int b = blockIdx.x, t = threadIdx.x;
+  Fp* summ = M + KD_THREADS;                     // [0], [1]: this CTA's (A, M) summary; [2]: carry into this CTA
+  const int rank = cs > 1 ? (int)cg::this_cluster().block_rank() : 0;
+  const int b = blockIdx.x / cs, t = threadIdx.x;
   const Fp* a = in + (long long)b * in_stride;
   Fp* q = out + (long long)b * out_stride;
-  Fp z = zs[(long long)b * z_stride];
-  int T = n < KD_THREADS ? n : KD_THREADS;
-  int m = n / T;  // chunk per thread (n, T powers of two)
-  // pass 1: chunk-local value at the bottom of the chunk with zero incoming carry; q index j in [t*m, (t+1)*m)
-  Fp loc = Fp::zero(), zm = Fp::one();
+  const Fp z = zs[(long long)b * z_stride];
+  const int T = (n / cs) < KD_THREADS ? (n / cs) : KD_THREADS;   // active threads per CTA
+  const int m = n / (cs * T);                                      // chunk per thread (powers of two, m <= KD_MAX_M)
+  const int j0 = (rank * T + t) * m;                               // q indices [j0, j0 + m)
+  Fp av[KD_MAX_M];
+  Fp loc = Fp::zero(), zm = z;
   if (t < T) {
-    for (int j = (t + 1) * m - 1; j >= t * m; --j) {
-      Fp aj1 = (j + 1 < n) ? ldg_fe(a + j + 1) : Fp::zero();
-      loc = aj1 + z * loc;
-      zm = zm * z;
-    }
+#pragma unroll
+    for (int i = 0; i < KD_MAX_M; ++i) { int j = j0 + i + 1; av[i] = (i < m && j < n) ? ldg_fe(a + j) : Fp::zero(); }
+#pragma unroll
+    for (int i = KD_MAX_M - 1; i >= 0; --i) if (i < m) loc = av[i] + z * loc;
+    for (int i = 1; i < m; i <<= 1) zm = zm.sqr();
     A[t] = loc; M[t] = zm;
   }
   __syncthreads();
-  // suffix composition: carry into chunk t-1 is C_{t-1} = A_t + M_t * C_t, C_{T-1} = 0
+  // suffix composition inside the CTA: carry into chunk t-1 is C_{t-1} = A_t + M_t * C_t
   for (int d = 1; d < T; d <<= 1) {
-    Fp na, nm; bool act = (t < T) && (t + d < T);
+    Fp na, nm; const bool act = (t < T) && (t + d < T);
     if (act) { na = A[t] + M[t] * A[t + d]; nm = M[t] * M[t + d]; }
     __syncthreads();
     if (act) { A[t] = na; M[t] = nm; }
     __syncthreads();
   }
-  // A[t] now equals q_{t*m} (the true value at the bottom of chunk t) = carry for chunk t-1
-  if (t < T) {
-    Fp carry = (t + 1 < T) ? A[t + 1] : Fp::zero();
-    Fp cur = carry;
-    for (int j = (t + 1) * m - 1; j >= t * m; --j) {
-      Fp aj1 = (j + 1 < n) ? ldg_fe(a + j + 1) : Fp::zero();
-      cur = aj1 + z * cur;
-      st_fe(q + j, cur);
+  // A[t]: value at the bottom of chunk t with zero carry into the top of this CTA; M[t] = z^(m (T - t))
+  Fp cin = Fp::zero();
+  if (cs > 1) {
+    cg::cluster_group cluster = cg::this_cluster();
+    if (t == 0) { summ[0] = A[0]; summ[1] = M[0]; }
+    cluster.sync();
+    if (t == 0) {
+      Fp c = Fp::zero();
+      for (int r = cs - 1; r > rank; --r) {
+        const Fp* rs = cluster.map_shared_rank(summ, r);
+        c = rs[0] + rs[1] * c;
+      }
+      summ[2] = c;
     }
+    __syncthreads();
+    cin = summ[2];
+    cluster.sync();   // nobody leaves while its summary may still be read
+  }
+  if (t < T) {
+    Fp cur = (t + 1 < T) ? A[t + 1] + M[t + 1] * cin : cin;
+#pragma unroll
+    for (int i = KD_MAX_M - 1; i >= 0; --i) if (i < m) { cur = av[i] + z * cur; st_fe(q + j0 + i, cur); }
   }
 }
 void poly_kate_div(Ctx* c, Fp* out, long long out_stride, const Fp* in, long long in_stride, const Fp* z, long long z_stride, int n, int B) {
   ProfScope prof_scope(c, PC_POLY);
   TB_REQUIRE((n & (n - 1)) == 0, "kate division needs a power-of-two length");
-  static bool attr = false;
-  if (!attr) { TB_CUDA(cudaFuncSetAttribute(kate_div_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * KD_THREADS * 32)); attr = true; }
-  kate_div_kernel<<<B, KD_THREADS, 2 * KD_THREADS * 32, c->stream>>>(out, out_stride, in, in_stride, z, z_stride, n);
+  const int cs = n >= KD_CLUSTER * KD_THREADS ? KD_CLUSTER : 1;
+  TB_REQUIRE(n / (cs * (n / cs < KD_THREADS ? n / cs : KD_THREADS)) <= KD_MAX_M, "kate division: polynomial too long for one cluster");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * cs)); cfg.blockDim = dim3(KD_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  TB_CUDA(cudaLaunchKernelEx(&cfg, kate_div_kernel, out, out_stride, in, in_stride, z, z_stride, n, cs));
   TB_LAUNCH_CHECK(); c->launches++;
 }
 
