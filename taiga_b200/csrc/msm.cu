@@ -66,15 +66,17 @@ __global__ void msm_digits_kernel(const S* __restrict__ scalars, long long sstri
   }
 }
 
-// units (chunks of <= chunk entries) per bucket; oversized buckets are appended to the heavy list
-__global__ void msm_units_kernel(const uint32_t* __restrict__ offs, uint32_t nb_total, uint32_t chunk_log, uint32_t* __restrict__ unit_count,
-                                 uint32_t* __restrict__ heavy, uint32_t* __restrict__ n_heavy) {
+// units (chunks of <= chunk entries) per bucket; buckets too large for the sub-warp combine go to the mid list (one warp
+// each), oversized ones to the heavy list (one CTA each)
+__global__ void msm_units_kernel(const uint32_t* __restrict__ offs, uint32_t nb_total, uint32_t chunk_log, uint32_t sub_units, uint32_t* __restrict__ unit_count,
+                                 uint32_t* __restrict__ mid, uint32_t* __restrict__ heavy, uint32_t* __restrict__ n_lists /* [0] mid, [1] heavy */) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb_total) return;
   uint32_t cnt = offs[b + 1] - offs[b];
   uint32_t uc = (cnt + (1u << chunk_log) - 1) >> chunk_log;
   unit_count[b] = uc;
-  if (uc > MSM_HEAVY_UNITS) heavy[atomicAdd(n_heavy, 1u)] = b;
+  if (uc > MSM_HEAVY_UNITS) heavy[atomicAdd(n_lists + 1, 1u)] = b;
+  else if (uc > sub_units) mid[atomicAdd(n_lists, 1u)] = b;
 }
 
 template <class B>
@@ -123,21 +125,18 @@ template <class B> __device__ Xyzz<B> block_reduce_pt(Xyzz<B> v, Xyzz<B>* sm /* 
   return v;
 }
 
-// one warp per bucket: sum the partial results of its units into a dense bucket array (warp-shuffle tree, only as deep as needed)
+// one warp per mid-list bucket (grid-stride): sum the partial results of its units (warp-shuffle tree)
 template <class B>
-__global__ void __launch_bounds__(256) msm_combine_kernel(const uint32_t* __restrict__ unit_off, const Xyzz<B>* __restrict__ partial, uint32_t nb_total,
-                                                           uint32_t serial_units, Xyzz<B>* __restrict__ buckets) {
-  uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (b >= nb_total) return;
-  uint32_t u0 = unit_off[b], u1 = unit_off[b + 1], units = u1 - u0;
-  if ((serial_units && units <= serial_units) || units > MSM_HEAVY_UNITS) return;  // handled by the serial / heavy kernels
-  Xyzz<B> acc = Xyzz<B>::inf();
-  for (uint32_t u = u0 + lane; u < u1; u += 32) acc.add(partial[u]);
-  if (units > 1) {
-    uint32_t live = units < 32 ? units : 32;
-    for (int d = 1 << (31 - __clz(live - 1)); d >= 1; d >>= 1) { Xyzz<B> o = shfl_down_pt(acc, d); acc.add(o); }
+__global__ void __launch_bounds__(256) msm_combine_kernel(const uint32_t* __restrict__ mid, const uint32_t* __restrict__ n_mid, const uint32_t* __restrict__ unit_off,
+                                                           const Xyzz<B>* __restrict__ partial, Xyzz<B>* __restrict__ buckets) {
+  const uint32_t lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5, nm = *n_mid;
+  for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nm; w += nw) {
+    const uint32_t b = mid[w], u0 = unit_off[b], u1 = unit_off[b + 1];
+    Xyzz<B> acc = Xyzz<B>::inf();
+    for (uint32_t u = u0 + lane; u < u1; u += 32) acc.add(partial[u]);
+    for (int d = 16; d >= 1; d >>= 1) { Xyzz<B> o = shfl_down_pt(acc, d); acc.add(o); }
+    if (lane == 0) buckets[b] = acc;
   }
-  if (lane == 0) buckets[b] = acc;
 }
 
 // 2^lpb_log lanes per bucket (1, 2, .. 32): every add a warp issues costs the same whether 1 or 32 of its lanes are live, so a
@@ -355,9 +354,18 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
     while ((1u << chunk_log) < (uint32_t)MSM_CHUNK_MAX && (max_entries >> chunk_log) > target_units) ++chunk_log; }
   const uint64_t max_units = nb_total64 + (max_entries >> chunk_log) + 1;
   const uint64_t max_heavy = (max_entries >> chunk_log) / MSM_HEAVY_UNITS + 1;
-  DevBuf<uint32_t> unit_count(ctx, nb_total), unit_off(ctx, nb_total + 1), heavy(ctx, max_heavy), n_heavy(ctx, 1);
-  n_heavy.zero();
-  msm_units_kernel<<<(nb_total + 255) / 256, 256, 0, st>>>(offs.get(), nb_total, chunk_log, unit_count.get(), heavy.get(), n_heavy.get());
+  // three disjoint classes of buckets: <= 4 * lanes units (a group of `lanes` threads), <= 1024 units (one warp), more (one
+  // CTA each).  lanes: as wide as keeps ~4 warps per SM sub-partition busy, no wider than the average bucket needs.
+  uint32_t lpb_log = 0;
+  { const uint64_t avg_units = ((max_entries >> chunk_log) + nb_total64 - 1) / nb_total64;
+    const uint64_t warps_target = (uint64_t)tb_tune("TB_MSM_SUB_WARPS_PER_SM", 16) * (uint64_t)ctx->sm_count;
+    while (lpb_log < 5 && ((nb_total64 << (lpb_log + 1)) >> 5) <= warps_target && (1ull << lpb_log) < avg_units) ++lpb_log; }
+  const uint32_t sub_units = 4u << lpb_log;
+  uint64_t max_mid = (max_entries >> chunk_log) / sub_units + 1;   // buckets with more than sub_units * chunk entries
+  if (max_mid > nb_total64) max_mid = nb_total64;
+  DevBuf<uint32_t> unit_count(ctx, nb_total), unit_off(ctx, nb_total + 1), mid(ctx, max_mid), heavy(ctx, max_heavy), n_lists(ctx, 2);
+  n_lists.zero();
+  msm_units_kernel<<<(nb_total + 255) / 256, 256, 0, st>>>(offs.get(), nb_total, chunk_log, sub_units, unit_count.get(), mid.get(), heavy.get(), n_lists.get());
   TB_LAUNCH_CHECK();
   exclusive_scan_u32(ctx, unit_count.get(), unit_off.get(), nb_total);
   DevBuf<Xyzz<B>> partial(ctx, max_units), buckets(ctx, nb_total);
@@ -366,19 +374,12 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
                                                                           nb_total, 1u << chunk_log, entries.get(), partial.get());
   TB_LAUNCH_CHECK();
   ps.reset(); ps.reset(new ProfScope(ctx, PC_MSM_REDUCE));
-  // three disjoint classes of buckets: <= 4 * lanes units (a group of `lanes` threads), <= 1024 units (one warp), more (one
-  // CTA each).  lanes: as wide as keeps ~4 warps per SM sub-partition busy, no wider than the average bucket needs.
-  uint32_t lpb_log = 0;
-  { const uint64_t avg_units = ((max_entries >> chunk_log) + nb_total64 - 1) / nb_total64;
-    const uint64_t warps_target = (uint64_t)tb_tune("TB_MSM_SUB_WARPS_PER_SM", 16) * (uint64_t)ctx->sm_count;
-    while (lpb_log < 5 && ((nb_total64 << (lpb_log + 1)) >> 5) <= warps_target && (1ull << lpb_log) < avg_units) ++lpb_log; }
-  const uint32_t sub_units = 4u << lpb_log;
   msm_combine_sub_kernel<B><<<(unsigned)((((uint64_t)nb_total << lpb_log) + 127) / 128), 128, 0, st>>>(unit_off.get(), partial.get(), nb_total, lpb_log,
                                                                                                       buckets.get());
-  if ((max_entries >> chunk_log) > sub_units)
-    msm_combine_kernel<B><<<(unsigned)(((uint64_t)nb_total * 32 + 255) / 256), 256, 0, st>>>(unit_off.get(), partial.get(), nb_total, sub_units, buckets.get());
+  { uint64_t g = (max_mid + 7) / 8, cap = 4ull * (uint64_t)ctx->sm_count;   // e.g. a witness column that is mostly small values
+    msm_combine_kernel<B><<<(unsigned)(g < cap ? g : cap), 256, 0, st>>>(mid.get(), n_lists.get(), unit_off.get(), partial.get(), buckets.get()); }
   if ((max_entries >> chunk_log) > MSM_HEAVY_UNITS)  // e.g. the top window of a variable-base MSM, or a witness column that is mostly ones
-    msm_combine_heavy_kernel<B><<<(unsigned)(max_heavy < 296 ? max_heavy : 296), 256, 0, st>>>(heavy.get(), n_heavy.get(), unit_off.get(), partial.get(), buckets.get());
+    msm_combine_heavy_kernel<B><<<(unsigned)(max_heavy < 296 ? max_heavy : 296), 256, 0, st>>>(heavy.get(), n_lists.get() + 1, unit_off.get(), partial.get(), buckets.get());
   TB_LAUNCH_CHECK();
 
   const int seg_t = tb_tune("TB_MSM_SEG", MSM_SEG);
