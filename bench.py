@@ -230,7 +230,7 @@ def main():
     nw = 2 if args.ptx <= 2 else 1   # small batches: two streams per circuit so latency-bound phases overlap
     if args.serial:
         nw = 1
-    svc = ptx.ProverService(local, srs, c_workers=nw, v_workers=nw, serial=args.serial)
+    svc = ptx.ProverService(local, srs, c_workers=int(os.environ.get("TB_C_WORKERS", nw)), v_workers=int(os.environ.get("TB_V_WORKERS", nw)), serial=args.serial)
     ctx = svc.ctx
     P = args.ptx
     wit = svc.synthesize_ptx(P, wseed=rank)

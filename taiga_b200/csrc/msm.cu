@@ -79,8 +79,8 @@ __global__ void msm_units_kernel(const uint32_t* __restrict__ offs, uint32_t nb_
   else if (uc > sub_units) mid[atomicAdd(n_lists, 1u)] = b;
 }
 
-template <class B>
-__global__ void __launch_bounds__(128) msm_accum_kernel(const Aff<B>* __restrict__ bases, long long base_bstride, uint32_t buckets_per_item,
+template <class B, int MINB>
+__global__ void __launch_bounds__(128, MINB) msm_accum_kernel(const Aff<B>* __restrict__ bases, long long base_bstride, uint32_t buckets_per_item,
                                  const uint32_t* __restrict__ offs, const uint32_t* __restrict__ unit_off, uint32_t nb_total, uint32_t chunk,
                                  const uint32_t* __restrict__ entries, Xyzz<B>* __restrict__ partial) {
   uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
@@ -370,8 +370,11 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
   exclusive_scan_u32(ctx, unit_count.get(), unit_off.get(), nb_total);
   DevBuf<Xyzz<B>> partial(ctx, max_units), buckets(ctx, nb_total);
   ps.reset(); ps.reset(new ProfScope(ctx, PC_MSM_ACCUM));
-  msm_accum_kernel<B><<<(unsigned)((max_units + 127) / 128), 128, 0, st>>>(bases, base_bstride, (uint32_t)wsep * NB, offs.get(), unit_off.get(),
-                                                                          nb_total, 1u << chunk_log, entries.get(), partial.get());
+  { const unsigned ag = (unsigned)((max_units + 127) / 128);
+    const int minb = tb_tune("TB_MSM_ACCUM_MINB", 4);
+    if (minb >= 6) msm_accum_kernel<B, 6><<<ag, 128, 0, st>>>(bases, base_bstride, (uint32_t)wsep * NB, offs.get(), unit_off.get(), nb_total, 1u << chunk_log, entries.get(), partial.get());
+    else if (minb == 5) msm_accum_kernel<B, 5><<<ag, 128, 0, st>>>(bases, base_bstride, (uint32_t)wsep * NB, offs.get(), unit_off.get(), nb_total, 1u << chunk_log, entries.get(), partial.get());
+    else msm_accum_kernel<B, 4><<<ag, 128, 0, st>>>(bases, base_bstride, (uint32_t)wsep * NB, offs.get(), unit_off.get(), nb_total, 1u << chunk_log, entries.get(), partial.get()); }
   TB_LAUNCH_CHECK();
   ps.reset(); ps.reset(new ProfScope(ctx, PC_MSM_REDUCE));
   msm_combine_sub_kernel<B><<<(unsigned)((((uint64_t)nb_total << lpb_log) + 127) / 128), 128, 0, st>>>(unit_off.get(), partial.get(), nb_total, lpb_log,
