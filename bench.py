@@ -187,10 +187,13 @@ def sweep(ctx, hbm_peak, quick):
 
 # DRAM traffic per launch of the dominant kernels from the committed ncu captures (profiles/r01_ncu_summary.md, capture B:
 # Compliance-shaped circuit, 2 proofs per launch = 20 advice MSMs resp. one sub-coset of 2 proofs)
-NCU_TRAFFIC = {
-    "msm_accum": {"dram_bytes_per_launch": 48.6e6, "algorithmic_bytes_same_launch": 20 * 96 * N15, "capture": "profiles/r01_ncu_summary.md capture B (K = 20 MSMs)"},
-    "quotient_gates": {"dram_bytes_per_launch": 40.6e6, "algorithmic_bytes_same_launch": 2 * 32 * 31 * N15, "capture": "profiles/r01_ncu_summary.md capture B (one sub-coset, 2 proofs)"},
-    "ntt": {"dram_bytes_per_launch": 21.2e6, "algorithmic_bytes_same_launch": 20 * 32 * N15, "capture": "profiles/r01_ncu_summary.md capture A (one pass, 20 columns: read 21 MB = algorithmic)"},
+NCU_TRAFFIC = {   # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from profiles/r01_ncu_summary.md capture C (ncu --set full)
+    "msm_accum": {"dram_bytes_per_launch": 47.56e6, "algorithmic_bytes_same_launch": 2 * 96 * N15,
+                  "capture": "capture C, K = 2 dense commitments: the 42 MB fixed-base window table is streamed once per launch (amortised over K; K = 20 read 48.6 MB vs 63 MB algorithmic in capture B)"},
+    "quotient_gates": {"dram_bytes_per_launch": 28.74e6, "algorithmic_bytes_same_launch": 32 * 28 * N15,
+                       "capture": "capture C, one sub-coset of one proof, 8 constraint parts: every column-coset is read from DRAM once, the other parts hit L2"},
+    "ntt": {"dram_bytes_per_launch": 15.92e6, "algorithmic_bytes_same_launch": 15 * 32 * N15,
+            "capture": "capture C, one pass over 15 columns: DRAM read = algorithmic read, the writes stay in the 126 MB L2"},
 }
 
 ALG_BYTES_NOTE = {
@@ -328,7 +331,8 @@ def main():
         roof["achieved"] = round(top_bytes / (top_ms * 1e-3) / 1e9, 2)
         roof["frac"] = round(roof["achieved"] / hbm_peak, 5)
     if top_name in NCU_TRAFFIC:
-        roof["traffic"] = NCU_TRAFFIC[top_name]
+        roof["traffic"] = NCU_TRAFFIC[top_name]["dram_bytes_per_launch"]
+        roof["traffic_detail"] = NCU_TRAFFIC[top_name]
     # the same figures for every kernel group of the step (the dominant one is repeated above)
     roof["per_kernel"] = {k: {"ms": round(v[0], 3), "groups": v[1], "achieved_gbs": (round(alg[k] / (v[0] * 1e-3) / 1e9, 2) if alg.get(k) and v[0] > 0 else None),
                               "frac": (round(alg[k] / (v[0] * 1e-3) / 1e9 / hbm_peak, 5) if alg.get(k) and v[0] > 0 else None)} for k, v in prof.items()}
