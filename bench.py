@@ -302,6 +302,12 @@ def main():
             all(kv.verify(wit["v_inst"][i], wit["v_len"], p) == 0 for i, p in enumerate(last_e2e[1]))
     except Exception as ex:  # pragma: no cover
         accepted = "verifier unavailable: %r" % (ex,)
+    # ... and under the library's own batched device verifier (tb_verify_batch)
+    try:
+        accepted_dev = all(svc.pk_c.verify_batch(wit["c_inst"], wit["c_len"], list(last_e2e[0]))) and \
+            all(svc.pk_v.verify_batch(wit["v_inst"], wit["v_len"], list(last_e2e[1]), ctx=svc.v_workers[0][0]))
+    except Exception as ex:  # pragma: no cover
+        accepted_dev = "device verifier failed: %r" % (ex,)
 
     hbm_peak, peak_kind = measured_peaks()
     total_ptx = P * world
@@ -342,7 +348,7 @@ def main():
         "dtype": "u32x8 (255-bit Montgomery integers, Pasta Fp/Fq)", "data": "synthetic",
         "config": {"workload": "%d shielded partial transaction(s) per GPU per step = %d Compliance-shaped (degree 17, ext 2^19, 4480 B proofs) + %d VP-shaped (degree 9) Halo2/IPA proofs, k=15, Taiga params_15 SRS (BASELINE configs[%d])"
                    % (P, 2 * P, 4 * P, 1 if P == 1 else 2), "ptx_per_gpu": P, "parallelism": "independent ptx per GPU (no collective inside a proof; NCCL all_gather of proof bytes); %d CUDA streams per circuit" % nw,
-                   "l2": "inputs (60 MiB advice per ptx + 0.9 GB resident key cosets) exceed L2; no explicit flush", "proofs_accepted_by_oracle_verifier": accepted},
+                   "l2": "inputs (60 MiB advice per ptx + 0.9 GB resident key cosets) exceed L2; no explicit flush", "proofs_accepted_by_oracle_verifier": accepted, "proofs_accepted_by_device_verifier": accepted_dev},
         "e2e": {"value": round(e2e_val, 4), "unit": "ptx/s", "ms_per_step": round(e2e_step_ms, 3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "device_event_ms_per_step": round(dev_ms / args.steps, 3),
         "gpu_launches": int(launches), "clocks": clocks,

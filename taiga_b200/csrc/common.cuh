@@ -28,7 +28,10 @@ struct ConstraintError : std::runtime_error { using std::runtime_error::runtime_
 // field and direction, L2 resident).  w_S^e = hi[e >> 12] * lo[e & 4095].
 constexpr int TW_LOG = 24;
 constexpr int TW_HALF = 12;
-template <class F> struct TwiddleTables { F* lo = nullptr; F* hi = nullptr; };
+// w_S^e, S = 2^24: two-level tables (e = hi * 2^12 + lo) plus, for the circuit field, a flat table of the 2^full_log-th roots --
+// every twiddle the k <= 19 prover NTTs and the quotient kernels ask for is then one 32-byte load instead of a load pair and a multiply
+template <class F> struct TwiddleTables { F* lo = nullptr; F* hi = nullptr; F* full = nullptr; int full_log = 0; };
+constexpr int TW_FULL_LOG = 19;
 
 template <class F> struct FieldTables {
   TwiddleTables<F> fwd, inv;
@@ -144,11 +147,15 @@ template <class F> __device__ __forceinline__ Aff<F> ldg_aff(const Aff<F>* p) {
   Aff<F> a; a.x = ldg_fe(&p->x); a.y = ldg_fe(&p->y); return a;
 }
 // w_S^e from the two-level table
-template <class F> __device__ __forceinline__ F tw_pow(const TwiddleTables<F>& t, uint32_t e) {
+template <class F> __device__ __forceinline__ F tw_pow2(const TwiddleTables<F>& t, uint32_t e) {
   F h = ldg_fe(t.hi + (e >> TW_HALF));
   uint32_t lo = e & ((1u << TW_HALF) - 1);
   if (lo) h = h * ldg_fe(t.lo + lo);
   return h;
+}
+template <class F> __device__ __forceinline__ F tw_pow(const TwiddleTables<F>& t, uint32_t e) {
+  if (t.full && (e & ((1u << (TW_LOG - TW_FULL_LOG)) - 1)) == 0) return ldg_fe(t.full + (e >> (TW_LOG - TW_FULL_LOG)));
+  return tw_pow2(t, e);
 }
 #endif
 

@@ -174,6 +174,12 @@ template void ntt_run<Fq>(Ctx*, int, bool, const Fq*, Fq*, Fq*, int, long long, 
 
 // ---- twiddle table construction (host arithmetic with the same field code, uploaded once per context)
 template <class F>
+__global__ void tw_fill_kernel(TwiddleTables<F> t, F* full) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (1u << TW_FULL_LOG)) st_fe(full + i, tw_pow2(t, i << (TW_LOG - TW_FULL_LOG)));
+}
+
+template <class F>
 void build_twiddles(Ctx* ctx) {
   FieldTables<F>& ft = field_tables<F>(ctx);
   F w = omega_k<F>(TW_LOG), wi = w.inv();
@@ -189,6 +195,14 @@ void build_twiddles(Ctx* ctx) {
     TB_CUDA(cudaMalloc(&t.hi, n * sizeof(F)));
     TB_CUDA(cudaMemcpy(t.lo, lo.data(), n * sizeof(F), cudaMemcpyHostToDevice));
     TB_CUDA(cudaMemcpy(t.hi, hi.data(), n * sizeof(F), cudaMemcpyHostToDevice));
+    if (F::params_id() == 0) {  // circuit field only: 2 x 16 MB per context
+      F* full = nullptr;
+      TB_CUDA(cudaMalloc(&full, sizeof(F) << TW_FULL_LOG));
+      tw_fill_kernel<F><<<(1u << TW_FULL_LOG) / 256, 256>>>(t, full);
+      TB_CUDA(cudaGetLastError());
+      TB_CUDA(cudaDeviceSynchronize());
+      t.full = full; t.full_log = TW_FULL_LOG;
+    }
   }
 }
 template void build_twiddles<Fp>(Ctx*);
@@ -197,7 +211,7 @@ template void build_twiddles<Fq>(Ctx*);
 template <class F>
 void free_twiddles(Ctx* ctx) {
   FieldTables<F>& ft = field_tables<F>(ctx);
-  cudaFree(ft.fwd.lo); cudaFree(ft.fwd.hi); cudaFree(ft.inv.lo); cudaFree(ft.inv.hi);
+  cudaFree(ft.fwd.lo); cudaFree(ft.fwd.hi); cudaFree(ft.inv.lo); cudaFree(ft.inv.hi); cudaFree(ft.fwd.full); cudaFree(ft.inv.full);
 }
 template void free_twiddles<Fp>(Ctx*);
 template void free_twiddles<Fq>(Ctx*);
