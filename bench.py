@@ -282,9 +282,13 @@ def main():
     e2e_ms, e2e_wall_ms, _, last_e2e = timed(False)
     clocks = sampler.summary()
 
-    # one profiled step (CUDA events around every kernel group) for the share-of-step table and the roofline
+    # one profiled step (CUDA events around every kernel group) for the share-of-step table and the roofline.  It runs the
+    # workers one after the other: with the streams overlapped an event pair also times the wait for SMs held by the other
+    # streams' kernels, and the shares would not be comparable with the (serialised) ncu launch list in profiles/.
     svc.prof_enable(True)
+    was_serial, svc.serial = svc.serial, True
     step(999, True)
+    svc.serial = was_serial
     prof = svc.prof_read()
     svc.prof_enable(False)
 
