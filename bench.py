@@ -123,7 +123,7 @@ def run_reference(args, rank, world):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (255-bit Montgomery integers)", "data": "synthetic",
             "config": {"workload": "1 shielded partial transaction = 2 Compliance-shaped + 4 VP-shaped Halo2/IPA proofs, k=15 (BASELINE configs[1]); CPU step = bounded sample 1C+1V extrapolated 2C+4V"},
             "cpu_baseline": dict(base, value=val), "e2e": {"value": val, "unit": "ptx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def sweep(ctx, hbm_peak, quick):
@@ -187,6 +187,18 @@ def sweep(ctx, hbm_peak, quick):
 
 # DRAM traffic per launch of the dominant kernels from the committed ncu captures (profiles/r01_ncu_summary.md, capture B:
 # Compliance-shaped circuit, 2 proofs per launch = 20 advice MSMs resp. one sub-coset of 2 proofs)
+# The contract is ONE JSON line on stdout.  Libraries may write to file descriptor 1 behind Python's back (NCCL prints its
+# version banner there when the communicator is created), so the real stdout is set aside at import time, everything
+# else that targets fd 1 is sent to stderr, and only emit() writes to the real one.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 NCU_TRAFFIC = {   # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from profiles/r01_ncu_summary.md capture C (ncu --set full)
     "msm_accum": {"dram_bytes_per_launch": 47.56e6, "algorithmic_bytes_same_launch": 2 * 96 * N15,
                   "capture": "capture C, K = 2 dense commitments: the 42 MB fixed-base window table is streamed once per launch (amortised over K; K = 20 read 48.6 MB vs 63 MB algorithmic in capture B)"},
@@ -387,7 +399,7 @@ def main():
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_prove_sample(srs)
         line["speedup_e2e_vs_cpu_port"] = round(e2e_val / line["cpu_baseline"]["value"], 2)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
