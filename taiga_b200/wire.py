@@ -17,6 +17,7 @@ bytes, fixed arrays raw, `Option` = 1 tag byte; field elements are their 32-byte
 The verifying key is an opaque byte string here: halo2's `VerifyingKey::write` belongs to the un-vendored fork, and its
 reader is self-delimiting only together with the circuit, so decoders take the vk length as a parameter.
 """
+import hashlib
 import struct
 
 P = 0x40000000000000000000000000000000224698FC094CF91B992D30ED00000001  # Pallas base field = circuit field
@@ -117,6 +118,13 @@ def compress_pallas(pt):
     if x == 0 and y == 0:
         return bytes(32)
     return (x | ((y & 1) << 255)).to_bytes(32, "little")
+
+
+# ---------------------------------------------------------------- ResourceLogicCommitment
+def resource_logic_commitment(resource_logic, rcm):
+    """ResourceLogicCommitment::commit (resource_logic_commitment.rs:18-27): BLAKE2s-256, personalisation "VPCommit", over the
+    32-byte little-endian encodings of the resource-logic verifying-key hash and the commitment randomness (both Fp)."""
+    return hashlib.blake2s(_fe_bytes(resource_logic) + _fe_bytes(rcm), digest_size=32, person=b"VPCommit").digest()
 
 
 # ---------------------------------------------------------------- CompliancePublicInputs

@@ -110,3 +110,12 @@ def test_malformed_records_are_rejected():
         wire.encode_rl_verifying_info(b"", b"", [0] * 21)
     with pytest.raises(wire.WireError):
         wire.encode_ptx([], [], [], pasta.Q, b"")
+
+
+def test_resource_logic_commitment_vector():
+    # the Blake2s chip equals blake2s_simd (blake2s.rs:1176-1210), so VPCommit vectors are regenerable;
+    # VPCommit(1, 1) as computed there
+    c = wire.resource_logic_commitment(1, 1)
+    assert c.hex() == "f8ad5e9e7bd488260e34366e3d00e29c3fd242d7e97f5237b698ca0f0e58dd9f"
+    lo, hi = wire.CompliancePublicInputs._rl_halves(c)
+    assert lo < (1 << 128) and hi < (1 << 128) and lo | (hi << 128) == int.from_bytes(c, "little")
