@@ -32,3 +32,21 @@ def test_fails_loudly_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(lib.TaigaB200Error):
         lib.Context(0)
+
+
+def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu(tmp_path):
+    """include/taiga_b200.hpp (the C++ mirror of Proof::create / Proof::verify over the C ABI) compiles with a plain host
+    compiler, links against the in-tree library, and its example reports the missing device as a typed error."""
+    import subprocess
+    import torch
+    exe = str(tmp_path / "prove_cpp")
+    libdir = os.path.dirname(lib.LIB_PATH)
+    cmd = ["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "prove_cpp.cpp"),
+           "-L", libdir, "-ltaiga_b200", "-Wl,-rpath," + libdir, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the no-device path cannot be exercised")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1
+    assert "no CPU fallback" in r.stderr and "BackendFailure" in r.stderr
