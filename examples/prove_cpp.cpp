@@ -7,10 +7,11 @@
 //
 //   g++ -std=c++17 -I include examples/prove_cpp.cpp -L taiga_b200 -ltaiga_b200 -Wl,-rpath,$PWD/taiga_b200 -o /tmp/prove_cpp
 #include <cstdio>
+#include <string>
 #include <vector>
 
 #define TB_PORTABLE_FIELD 1
-#include "../taiga_b200/csrc/field.cuh"
+#include "../taiga_b200/csrc/curve.cuh"
 #include "taiga_b200.hpp"
 
 using namespace taiga_b200;
@@ -24,20 +25,61 @@ static FieldBytes to_bytes(const Fp& v) {
 }
 static Fp small(uint32_t v) { return Fp::from_u32(v); }
 
-int main() {
+// omega_k = ROOT_OF_UNITY^(2^(32-k)), ROOT_OF_UNITY = 5^((p-1)/2^32)   (pasta_curves Fp constants)
+static Fp omega_of(uint32_t k) {
+  const uint32_t t[8] = {0x992d30edu, 0x094cf91bu, 0x224698fcu, 0, 0, 0, 0x40000000u, 0};   // (p - 1) >> 32
+  Fp root = Fp::one(), base = small(5);
+  for (int limb = 7; limb >= 0; --limb) for (int bit = 31; bit >= 0; --bit) { root = root.sqr(); if ((t[limb] >> bit) & 1) root = root * base; }
+  for (uint32_t i = 0; i < 32 - k; ++i) root = root.sqr();
+  return root;
+}
+static PointBytes point_bytes(const tb::Aff<tb::Fq>& a) {
+  PointBytes out;
+  tb::Fq x = a.x.from_mont(), y = a.y.from_mont();
+  for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) { out[4 * i + j] = (uint8_t)(x.l[i] >> (8 * j)); out[32 + 4 * i + j] = (uint8_t)(y.l[i] >> (8 * j)); }
+  return out;
+}
+static PointBytes mul_generator(const Fp& scalar) {
+  tb::Aff<tb::Fq> G;   // Vesta generator (-1, 2)
+  G.x = tb::Fq::one().neg(); G.y = tb::Fq::from_u32(2);
+  Fp c = scalar.from_mont();
+  return point_bytes(tb::scalar_mul(G, c.l).to_affine());
+}
+static void build_srs(uint32_t k, const Fp& omega, std::vector<uint8_t>& g, std::vector<uint8_t>& gl, PointBytes& W, PointBytes& U) {
+  const uint32_t n = 1u << k;
+  const Fp s = small(0x5eed5eedu) * small(0x0badc0deu) + small(7);
+  Fp sn = s;
+  for (uint32_t i = 0; i < k; ++i) sn = sn.sqr();                       // s^n
+  const Fp num = (sn - Fp::one()) * small(n).inv();                     // (s^n - 1) / n
+  Fp sj = Fp::one(), wi = Fp::one();
+  for (uint32_t i = 0; i < n; ++i) {
+    PointBytes a = mul_generator(sj), b = mul_generator(wi * num * (s - wi).inv());
+    std::memcpy(&g[64 * i], a.data(), 64); std::memcpy(&gl[64 * i], b.data(), 64);
+    sj = sj * s; wi = wi * omega;
+  }
+  W = mul_generator(small(0x77777777u) * small(0x12345u));
+  U = mul_generator(small(0x33333333u) * small(0x54321u));
+}
+
+int main(int argc, char** argv) {
   try {
     const uint32_t k = 5, n = 1u << k;
-    Context ctx(0);   // throws without a usable sm_100 device
-
-    // ---- a throw-away SRS: g_i = [s_i] G is not computable on the host without curve code, so this example uses the
-    // generator for every basis point.  (Binding is irrelevant for a smoke run; real callers pass params_15.)
+    const Fp omega = omega_of(k);
     std::vector<uint8_t> g(64 * n), gl(64 * n);
-    PointBytes G{};   // Vesta generator (-1, 2): x = q - 1, y = 2
-    { const uint32_t qm1[8] = {0x00000000u, 0x8c46eb21u, 0x0994a8ddu, 0x224698fcu, 0, 0, 0, 0x40000000u};
-      for (int i = 0; i < 8; ++i) for (int j = 0; j < 4; ++j) G[4 * i + j] = (uint8_t)(qm1[i] >> (8 * j));
-      G[32] = 2; }
-    for (uint32_t i = 0; i < n; ++i) { std::memcpy(&g[64 * i], G.data(), 64); std::memcpy(&gl[64 * i], G.data(), 64); }
-    Params params(ctx, k, g.data(), gl.data(), G, G);
+    PointBytes W{}, U{};
+    // ---- a throw-away SRS with the structure Params::new produces: g_lagrange is the Lagrange-basis image of g, i.e.
+    // sum_i v_i * g_lagrange[i] == sum_j c_j * g[j] whenever c = iNTT(v).  Here g[j] = [s^j] G for a fixed scalar s (fine for
+    // an example, worthless as a commitment key), hence g_lagrange[i] = [L_i(s)] G with
+    // L_i(s) = omega^i (s^n - 1) / (n (s - omega^i)); w = [s_w] G, u = [s_u] G.
+    build_srs(k, omega, g, gl, W, U);
+    if (argc > 2 && std::string(argv[1]) == "--dump-srs") {   // lets tests/test_abi.py check the construction on a CPU-only box
+      FILE* f = std::fopen(argv[2], "wb");
+      if (!f) return 3;
+      std::fwrite(g.data(), 1, g.size(), f); std::fwrite(gl.data(), 1, gl.size(), f); std::fwrite(W.data(), 1, 64, f); std::fwrite(U.data(), 1, 64, f);
+      std::fclose(f);
+    }
+    Context ctx(0);   // throws without a usable sm_100 device
+    Params params(ctx, k, g.data(), gl.data(), W, U);
 
     // ---- constraint system
     ConstraintSystem cs;
@@ -55,16 +97,6 @@ int main() {
     // ---- key material: selector on row 0; sigma = identity (delta^col * omega^row) with c[0] <-> instance[0] swapped
     std::vector<uint8_t> fixed(32 * n, 0), sigma(32 * n * 4);
     { FieldBytes one = to_bytes(Fp::one()); std::memcpy(&fixed[0], one.data(), 32); }
-    Fp omega = Fp::one();
-    { // omega_k = ROOT_OF_UNITY^(2^(32-k)), ROOT_OF_UNITY = 5^((p-1)/2^32);  delta = 5^(2^32)
-      Fp root = Fp::one();
-      // (p - 1) / 2^32 as 7 limbs: p = 2^254 + 0x224698fc094cf91b992d30ed00000001
-      const uint32_t t[8] = {0x992d30edu, 0x094cf91bu, 0x224698fcu, 0, 0, 0, 0x40000000u, 0};
-      Fp base = small(5);
-      for (int limb = 7; limb >= 0; --limb) for (int bit = 31; bit >= 0; --bit) { root = root.sqr(); if ((t[limb] >> bit) & 1) root = root * base; }
-      omega = root;
-      for (uint32_t i = 0; i < 32 - k; ++i) omega = omega.sqr();
-    }
     Fp delta = small(5);
     for (int i = 0; i < 32; ++i) delta = delta.sqr();
     std::vector<Fp> sig(4 * n);

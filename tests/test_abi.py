@@ -47,6 +47,16 @@ def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu(tmp_path):
     assert r.returncode == 0, r.stderr
     if torch.cuda.is_available():
         pytest.skip("GPU present: the no-device path cannot be exercised")
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    dump = str(tmp_path / "srs.bin")
+    r = subprocess.run([exe, "--dump-srs", dump], capture_output=True, text=True, timeout=120)
     assert r.returncode == 1
     assert "no CPU fallback" in r.stderr and "BackendFailure" in r.stderr
+    # the key material the example builds with the library's host-mode field / curve code is a well-formed SRS
+    import random
+    from oracle import pasta as o
+    raw, n = open(dump, "rb").read(), 32
+    pts = [(int.from_bytes(raw[64 * i:64 * i + 32], "little"), int.from_bytes(raw[64 * i + 32:64 * i + 64], "little")) for i in range(2 * n + 2)]
+    assert all(o.VESTA.is_on_curve(p) for p in pts)
+    g, gl = pts[:n], pts[n:2 * n]
+    v = [random.Random(7).randrange(o.P) for _ in range(n)]
+    assert o.VESTA.msm(v, gl) == o.VESTA.msm(o.intt(v, o.omega(5)), g)     # commit_lagrange(values) == commit(coefficients)
