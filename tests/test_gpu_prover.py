@@ -1,7 +1,11 @@
 """GPU parity tests of the full prover (through tb_circuit_load / tb_prove_batch): proof bytes must equal the CPU
 oracle's byte for byte for the same seed, and must be accepted by the oracle's verifier restatement."""
+import os
+
 import numpy as np
 import pytest
+
+from conftest import GOLDEN
 
 from taiga_b200 import circuits_mini as cm
 from taiga_b200 import lib
@@ -39,6 +43,8 @@ def test_mini_circuit_proofs_bit_identical(gpu_ctx, oracle_cpu, k, wide, nl):
             first = next(i for i in range(len(ref)) if proofs[b][i] != ref[i])
             pytest.fail("proof %d differs from the oracle at byte %d (32-byte element %d)" % (b, first, first // 32))
         assert okey.verify(wit[b][1], lens, proofs[b]) == 0
+    if (k, wide, nl) == (6, False, 2):   # committed golden vector (tests/golden/make_proof_fixtures.py: witness 100, proof index 5)
+        assert proofs[0] == open(os.path.join(GOLDEN, "proof_k6_plonk.bin"), "rb").read()
 
 
 def test_unsatisfied_lookup_is_reported(gpu_ctx, oracle_cpu):

@@ -1,8 +1,12 @@
 """GPU parity at the reference's real size (k = 15, Taiga's own SRS fixture): the Compliance-shaped (degree 17,
 extended domain 2^19, 4480-byte proofs as in taiga_api.rs:109) and the Resource-Logic-shaped (degree 9) circuits.
 Proofs from the CUDA prover must equal the CPU oracle's byte for byte and be accepted by its verifier."""
+import os
+
 import numpy as np
 import pytest
+
+from conftest import GOLDEN
 
 from taiga_b200 import circuits_taiga as ct
 
@@ -32,6 +36,9 @@ def test_taiga_shape_proofs_bit_identical(gpu_ctx, gpu_srs, oracle_cpu, srs_fixt
     if proofs[1] != ref:
         first = next(i for i in range(len(ref)) if proofs[1][i] != ref[i])
         pytest.fail("GPU proof differs from the oracle at byte %d (element %d)" % (first, first // 32))
+    # ... and the committed golden vector of the same inputs (tests/golden/make_proof_fixtures.py: witness 41, proof index 1)
+    golden = open(os.path.join(GOLDEN, "proof_k15_compliance_shape.bin" if compliance else "proof_k15_vp_shape.bin"), "rb").read()
+    assert proofs[1] == golden
     # tampering is rejected
     bad = bytearray(proofs[0]); bad[40] ^= 1
     assert okey.verify(wit[0][1], lens, bytes(bad)) != 0

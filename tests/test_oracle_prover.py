@@ -66,3 +66,27 @@ def test_taiga_shapes_structure():
     asg = make_c(3)
     assert len(asg.instance[0]) == 9                                # CompliancePublicInputs::to_instance, compliance.rs:62-78
     assert kd_c.shape.rows_used > (1 << 14)                         # blake2s forces k = 15
+
+
+def test_golden_proofs_are_reproduced(oracle_cpu):
+    """tests/golden/proof_*.bin (made by tests/golden/make_proof_fixtures.py): the oracle must still produce exactly these
+    bytes for the same circuit, witness, SRS and seed, and accept them -- a change of one byte anywhere in the restated
+    prover shows up here on CPU.  The GPU suites compare the CUDA prover with the same files."""
+    import hashlib
+    import importlib.util
+    import json
+    import os
+    from conftest import GOLDEN
+    spec = importlib.util.spec_from_file_location("make_proof_fixtures", os.path.join(GOLDEN, "make_proof_fixtures.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    meta = json.load(open(os.path.join(GOLDEN, "proofs.json")))
+    seen = 0
+    for name, kd, srs, (adv, inst, lens), seed, idx in mk.cases(oracle_cpu):
+        want = open(os.path.join(GOLDEN, name), "rb").read()
+        assert hashlib.sha256(want).hexdigest() == meta[name]["sha256"] and len(want) == meta[name]["bytes"] == kd.proof_size()
+        key = oracle_cpu.OracleKey(kd, srs)
+        assert key.prove(adv, inst, lens, seed, proof_index=idx) == want
+        assert key.verify(inst, lens, want) == 0
+        seen += 1
+    assert seen == 3 and len(open(os.path.join(GOLDEN, "proof_k15_compliance_shape.bin"), "rb").read()) == 4480   # taiga_api.rs:109
