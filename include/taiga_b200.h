@@ -45,6 +45,9 @@ int tb_prof_categories(void);
 const char* tb_prof_category_name(int category);
 tb_status tb_prof_enable(tb_ctx* ctx, int on);
 tb_status tb_prof_read(tb_ctx* ctx, double* ms_out, uint64_t* counts_out);
+/* 255-bit Montgomery multiplications executed per category since the last call (the path is bound by the integer pipe, so
+ * this is the numerator of its roofline; see bench.py int_util).  Synchronises. */
+tb_status tb_prof_work(tb_ctx* ctx, double* modmuls_out);
 
 /* ---- primitives over HOST buffers (copies in and out inside the call).
  * tb_ntt   replaces halo2_proofs arithmetic::best_fft / EvaluationDomain::{lagrange_to_coeff, coeff_to_lagrange}

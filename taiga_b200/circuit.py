@@ -155,7 +155,7 @@ class ConstraintSystem:
 
     # ---- derived quantities (halo2 plonk/circuit.rs)
     def degree(self):
-        d = 3 if self.perm_columns else 1
+        d = 3   # permutation.required_degree() is 3 whether or not any column is equality-enabled (halo2 plonk/circuit.rs)
         for lk in self.lookups:
             ind = max([1] + [i.degree for i, _ in lk])
             td = max([1] + [t.degree for _, t in lk])

@@ -29,6 +29,8 @@ tb_status tb_ctx_create(int device, tb_ctx** out) {
     TB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thresh = UINT64_MAX;
     TB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    TB_CUDA(cudaMalloc(&ctx->c.d_msm_adds, sizeof(unsigned long long)));
+    TB_CUDA(cudaMemset(ctx->c.d_msm_adds, 0, sizeof(unsigned long long)));
     build_twiddles<Fp>(&ctx->c);
     build_twiddles<Fq>(&ctx->c);
   } catch (const std::exception& e) {
@@ -45,6 +47,7 @@ void tb_ctx_destroy(tb_ctx* ctx) {
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
   free_twiddles<Fp>(&ctx->c); free_twiddles<Fq>(&ctx->c);
+  cudaFree(ctx->c.d_msm_adds);
   cudaStreamDestroy(ctx->c.stream);
   delete ctx;
 }
@@ -75,6 +78,19 @@ tb_status tb_prof_read(tb_ctx* ctx, double* ms_out, uint64_t* counts_out) {
     ctx->c.event_pool.push_back(r.a); ctx->c.event_pool.push_back(r.b);
   }
   ctx->c.prof_recs.clear();
+  TB_API_END(ctx)
+}
+
+// Montgomery multiplications executed per category since the last call (analytic counts per launch; the batched MSM's bucket
+// additions are counted on the device and charged 6 multiplications each + the product tree)
+tb_status tb_prof_work(tb_ctx* ctx, double* modmuls_out) {
+  TB_API_BEGIN(ctx)
+  ctx->c.sync();
+  unsigned long long adds = 0;
+  TB_CUDA(cudaMemcpy(&adds, ctx->c.d_msm_adds, sizeof(adds), cudaMemcpyDeviceToHost));
+  TB_CUDA(cudaMemset(ctx->c.d_msm_adds, 0, sizeof(adds)));
+  ctx->c.work[PC_MSM_ACCUM] += 6.4 * (double)adds;
+  for (int i = 0; i < PC_COUNT; ++i) { modmuls_out[i] = ctx->c.work[i]; ctx->c.work[i] = 0; }
   TB_API_END(ctx)
 }
 

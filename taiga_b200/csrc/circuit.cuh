@@ -1,7 +1,10 @@
 // The device-resident proving key of one circuit (tb_pk) shared by prover.cu and verifier.cu.
 #pragma once
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <set>
+#include <memory>
 #include <vector>
 #include "prover_kernels.cuh"
 
@@ -11,6 +14,10 @@ enum PolyKind { PK_INST = 0, PK_ADV, PK_PZ, PK_LZ, PK_LPIN, PK_LPTAB, PK_FIXED, 
 struct PolyId { int kind, idx; bool operator<(const PolyId& o) const { return kind != o.kind ? kind < o.kind : idx < o.idx; } bool operator==(const PolyId& o) const { return kind == o.kind && idx == o.idx; } };
 struct QueryRef { PolyId poly; int rot; };
 struct WsBlock { void* p = nullptr; size_t bytes = 0; };
+// Scratch of one (context, batch size) pair: device blocks in request order and the small tables uploaded on first use.
+// A tb_pk may be shared by several contexts (= host threads); each gets its own workspace, and a second thread entering
+// with the SAME context and batch size while a call is in flight is refused (TB_ERR_INVALID) instead of corrupting it.
+struct ProveWs { std::vector<WsBlock> blocks; std::vector<void*> tables; std::vector<std::vector<uint8_t>> table_bytes; std::atomic<int> busy{0}; };
 
 struct Circuit {
   Ctx* ctx; const Srs* srs;
@@ -35,13 +42,18 @@ struct Circuit {
   std::vector<PolyId> uniq; std::vector<int> uniq_set; std::vector<std::vector<int>> point_sets;
   uint32_t proof_len;
   // persistent per-batch-size workspace and cached small tables (see prove_batch)
-  mutable std::map<int, std::vector<WsBlock>> ws;
-  mutable std::map<int, std::vector<void*>> cached_tables;
+  mutable std::mutex mu;                                                   // guards the two caches below
+  mutable std::map<std::pair<const Ctx*, int>, std::unique_ptr<ProveWs>> ws;
   mutable std::vector<Aff<Fq>> vk_fixed, vk_sigma;   // verifying-key commitments (Montgomery, host), filled on first verification
+  ProveWs& workspace(const Ctx* c, int B) const {
+    std::lock_guard<std::mutex> lk(mu);
+    auto& slot = ws[std::make_pair(c, B)];
+    if (!slot) slot.reset(new ProveWs());
+    return *slot;
+  }
 
   ~Circuit() {
-    for (auto& kv : ws) for (auto& b : kv.second) cudaFree(b.p);
-    for (auto& kv : cached_tables) for (void* p : kv.second) cudaFree(p);
+    for (auto& kv : ws) { for (auto& b : kv.second->blocks) cudaFree(b.p); for (void* p : kv.second->tables) cudaFree(p); }
     for (void* p : {(void*)fixed_vals, (void*)fixed_polys, (void*)fixed_cosets, (void*)sig_vals, (void*)sig_polys, (void*)sig_cosets, (void*)l0, (void*)l_last,
                     (void*)l_blind, (void*)consts, (void*)wr_inv, (void*)d_aq, (void*)d_fq, (void*)d_iq, (void*)d_perm, (void*)prog_gates.dev, (void*)prog_lookups.dev})
       if (p) cudaFree(p);

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <set>
 #include <vector>
 #include "curve.cuh"
 
@@ -54,6 +55,10 @@ struct Ctx {
   int sm_count = 148;
   uint64_t launches = 0;  // kernels launched through this context (bench's gpu_launches)
   bool prof = false; std::vector<ProfRec> prof_recs; std::vector<cudaEvent_t> event_pool;
+  // executed 255-bit Montgomery multiplications per kernel category (host-side accounting at every launch, for the integer-pipe
+  // roofline of bench.py); the bucket additions of the batched MSM are counted on the device (they depend on the scalars)
+  double work[PC_COUNT] = {0};
+  unsigned long long* d_msm_adds = nullptr;
   cudaEvent_t get_event() {
     cudaEvent_t e;
     if (!event_pool.empty()) { e = event_pool.back(); event_pool.pop_back(); return e; }
@@ -67,6 +72,13 @@ struct Ctx {
     return reinterpret_cast<T*>(p);
   }
   void free(void* p) { if (p) cudaFreeAsync(p, stream); }
+  // Opt a kernel into more than 48 KB of dynamic shared memory.  The attribute belongs to the (function, device) pair, so the
+  // "already done" set lives in the context (= one device), not in a process-wide static.
+  std::set<const void*> smem_opted;
+  template <class K> void opt_in_smem(K kernel, size_t bytes) {
+    if (smem_opted.insert(reinterpret_cast<const void*>(kernel)).second)
+      TB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  }
   void sync() { TB_CUDA(cudaStreamSynchronize(stream)); }
 };
 

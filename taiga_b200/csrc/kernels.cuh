@@ -33,6 +33,11 @@ int msm_default_window(int n, bool fixed_tables);
 template <class B, class S>
 void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>* bases, long long base_bstride, int N, int K,
              const MsmConfig& cfg, Xyzz<B>* out);
+// msm_batch.cu: throughput path for K fixed-base MSMs (shared-memory counting sort + batch-affine reduction rounds)
+bool msm_batch_applicable(int N, int K, const MsmConfig& cfg, int c);
+template <class B, class S>
+void msm_batch_buckets(Ctx* ctx, const S* scalars, long long sstride, const Aff<B>* table, int N, int K, int c, int W, int table_stride, const S* extras, int n_extra,
+                       Xyzz<B>* buckets);
 // table[w][i] = 2^(c*w) * bases[i], w < windows  (one-off, at SRS load)
 template <class B> void msm_build_tables(Ctx* ctx, const Aff<B>* bases, int N, int c, int windows, Aff<B>* table);
 template <class B> void points_to_affine(Ctx* ctx, const Xyzz<B>* acc, int K, Aff<B>* out);

@@ -67,8 +67,7 @@ __global__ void bitonic_global_kernel(Fp* keys, int n, int k, int j) {
 void sort_keys(Ctx* c, Fp* keys, int n, int arrays) {
   ProfScope prof_scope(c, PC_LOOKUP_SORT);
   TB_REQUIRE((n & (n - 1)) == 0, "sort needs a power-of-two length");
-  static bool attr = false;
-  if (!attr) { TB_CUDA(cudaFuncSetAttribute(bitonic_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_TILE * 32)); attr = true; }
+  c->opt_in_smem(bitonic_local_kernel, BS_TILE * 32);
   int tile = n < BS_TILE ? n : BS_TILE;
   dim3 lg(n / tile, arrays);
   bitonic_local_kernel<<<lg, BS_THREADS, tile * 32, c->stream>>>(keys, n, tile, 1, 0, 0);
@@ -134,8 +133,8 @@ __global__ void __launch_bounds__(LP_THREADS) lookup_arrange_kernel(const Fp* __
   int tot_rep = tot_first;
   (void)block_excl_scan(n_cons, sm, &tot_cons);
   // every distinct input value must consume one table copy (else Error::ConstraintSystemFailure)
-  if (t == 0 && tot_cons != usable - tot_rep) atomicOr(err, 1u);
-  if (tot_left != tot_rep) { if (t == 0) atomicOr(err, 1u); return; }
+  if (t == 0 && tot_cons != usable - tot_rep) err[blockIdx.x] = 1u;   // err: one flag per array = per (proof, lookup)
+  if (tot_left != tot_rep) { if (t == 0) err[blockIdx.x] = 1u; return; }
   int r = off_left;
   for (int i = i0; i < i1; ++i) {
     Fp v = ld_fe(T + i);

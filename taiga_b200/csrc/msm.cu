@@ -336,54 +336,67 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
   const uint32_t nb_total = (uint32_t)nb_total64;
   cudaStream_t st = ctx->stream;
 
-  DevBuf<uint32_t> counts(ctx, nb_total), offs(ctx, nb_total + 1), cursor(ctx, nb_total), entries(ctx, max_entries);
-  std::unique_ptr<ProfScope> ps(new ProfScope(ctx, PC_MSM_SORT));
-  counts.zero();
-  dim3 dg((N + n_extra + 255) / 256, K);
-  const S* extras = reinterpret_cast<const S*>(cfg_in.extra_scalars);
-  msm_digits_kernel<S, 0><<<dg, 256, 0, st>>>(scalars, scalar_bstride, N, c, W, NB, wsep, table_mode, table_stride, extras, n_extra, counts.get(), nullptr);
-  TB_LAUNCH_CHECK();
-  exclusive_scan_u32(ctx, counts.get(), offs.get(), nb_total);
-  TB_CUDA(cudaMemcpyAsync(cursor.get(), offs.get(), nb_total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-  msm_digits_kernel<S, 1><<<dg, 256, 0, st>>>(scalars, scalar_bstride, N, c, W, NB, wsep, table_mode, table_stride, extras, n_extra, cursor.get(), entries.get());
-  TB_LAUNCH_CHECK();
+  DevBuf<Xyzz<B>> buckets(ctx, nb_total);
+  ctx->work[PC_MSM_SORT] += 2.0 * (double)K * (N + n_extra);                      // two passes of from_mont over the scalars
+  ctx->work[PC_MSM_REDUCE] += (double)K * wsep * NB * 30.0;                       // ~2 full XYZZ additions (14 M) per bucket + the weighted tail
+  std::unique_ptr<ProfScope> ps;
+  if (msm_batch_applicable(N, K, cfg_in, c)) {
+    // throughput path: shared-memory counting sort per MSM + batch-affine pairwise reduction (msm_batch.cu)
+    msm_batch_buckets<B, S>(ctx, scalars, scalar_bstride, bases, N, K, c, W, table_stride, reinterpret_cast<const S*>(cfg_in.extra_scalars), n_extra, buckets.get());
+    ctx->launches -= 6;   // the fixed count added below covers the latency path's sort / accumulate launches
+  } else {
+    DevBuf<uint32_t> counts(ctx, nb_total), offs(ctx, nb_total + 1), cursor(ctx, nb_total), entries(ctx, max_entries);
+    ps.reset(new ProfScope(ctx, PC_MSM_SORT));
+    counts.zero();
+    dim3 dg((N + n_extra + 255) / 256, K);
+    const S* extras = reinterpret_cast<const S*>(cfg_in.extra_scalars);
+    msm_digits_kernel<S, 0><<<dg, 256, 0, st>>>(scalars, scalar_bstride, N, c, W, NB, wsep, table_mode, table_stride, extras, n_extra, counts.get(), nullptr);
+    TB_LAUNCH_CHECK();
+    exclusive_scan_u32(ctx, counts.get(), offs.get(), nb_total);
+    TB_CUDA(cudaMemcpyAsync(cursor.get(), offs.get(), nb_total * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    msm_digits_kernel<S, 1><<<dg, 256, 0, st>>>(scalars, scalar_bstride, N, c, W, NB, wsep, table_mode, table_stride, extras, n_extra, cursor.get(), entries.get());
+    TB_LAUNCH_CHECK();
 
-  // adaptive chunk: aim at ~4 waves of 512 threads per SM so that small batches still fill the machine
-  uint32_t chunk_log = 3;
-  { const uint64_t target_units = (uint64_t)tb_tune("TB_MSM_UNITS_PER_SM", 2048) * (uint64_t)ctx->sm_count;
-    while ((1u << chunk_log) < (uint32_t)MSM_CHUNK_MAX && (max_entries >> chunk_log) > target_units) ++chunk_log; }
-  const uint64_t max_units = nb_total64 + (max_entries >> chunk_log) + 1;
-  const uint64_t max_heavy = (max_entries >> chunk_log) / MSM_HEAVY_UNITS + 1;
-  // three disjoint classes of buckets: <= 4 * lanes units (a group of `lanes` threads), <= 1024 units (one warp), more (one
-  // CTA each).  lanes: as wide as keeps ~4 warps per SM sub-partition busy, no wider than the average bucket needs.
-  uint32_t lpb_log = 0;
-  { const uint64_t avg_units = ((max_entries >> chunk_log) + nb_total64 - 1) / nb_total64;
-    const uint64_t warps_target = (uint64_t)tb_tune("TB_MSM_SUB_WARPS_PER_SM", 16) * (uint64_t)ctx->sm_count;
-    while (lpb_log < 5 && ((nb_total64 << (lpb_log + 1)) >> 5) <= warps_target && (1ull << lpb_log) < avg_units) ++lpb_log; }
-  const uint32_t sub_units = 4u << lpb_log;
-  uint64_t max_mid = (max_entries >> chunk_log) / sub_units + 1;   // buckets with more than sub_units * chunk entries
-  if (max_mid > nb_total64) max_mid = nb_total64;
-  DevBuf<uint32_t> unit_count(ctx, nb_total), unit_off(ctx, nb_total + 1), mid(ctx, max_mid), heavy(ctx, max_heavy), n_lists(ctx, 2);
-  n_lists.zero();
-  msm_units_kernel<<<(nb_total + 255) / 256, 256, 0, st>>>(offs.get(), nb_total, chunk_log, sub_units, unit_count.get(), mid.get(), heavy.get(), n_lists.get());
-  TB_LAUNCH_CHECK();
-  exclusive_scan_u32(ctx, unit_count.get(), unit_off.get(), nb_total);
-  DevBuf<Xyzz<B>> partial(ctx, max_units), buckets(ctx, nb_total);
-  ps.reset(); ps.reset(new ProfScope(ctx, PC_MSM_ACCUM));
-  { const unsigned ag = (unsigned)((max_units + 127) / 128);
-    const int minb = tb_tune("TB_MSM_ACCUM_MINB", 4);
-    if (minb >= 6) msm_accum_kernel<B, 6><<<ag, 128, 0, st>>>(bases, base_bstride, (uint32_t)wsep * NB, offs.get(), unit_off.get(), nb_total, 1u << chunk_log, entries.get(), partial.get());
-    else if (minb == 5) msm_accum_kernel<B, 5><<<ag, 128, 0, st>>>(bases, base_bstride, (uint32_t)wsep * NB, offs.get(), unit_off.get(), nb_total, 1u << chunk_log, entries.get(), partial.get());
-    else msm_accum_kernel<B, 4><<<ag, 128, 0, st>>>(bases, base_bstride, (uint32_t)wsep * NB, offs.get(), unit_off.get(), nb_total, 1u << chunk_log, entries.get(), partial.get()); }
-  TB_LAUNCH_CHECK();
-  ps.reset(); ps.reset(new ProfScope(ctx, PC_MSM_REDUCE));
-  msm_combine_sub_kernel<B><<<(unsigned)((((uint64_t)nb_total << lpb_log) + 127) / 128), 128, 0, st>>>(unit_off.get(), partial.get(), nb_total, lpb_log,
-                                                                                                      buckets.get());
-  { uint64_t g = (max_mid + 7) / 8, cap = 4ull * (uint64_t)ctx->sm_count;   // e.g. a witness column that is mostly small values
-    msm_combine_kernel<B><<<(unsigned)(g < cap ? g : cap), 256, 0, st>>>(mid.get(), n_lists.get(), unit_off.get(), partial.get(), buckets.get()); }
-  if ((max_entries >> chunk_log) > MSM_HEAVY_UNITS)  // e.g. the top window of a variable-base MSM, or a witness column that is mostly ones
-    msm_combine_heavy_kernel<B><<<(unsigned)(max_heavy < 296 ? max_heavy : 296), 256, 0, st>>>(heavy.get(), n_lists.get() + 1, unit_off.get(), partial.get(), buckets.get());
-  TB_LAUNCH_CHECK();
+    // adaptive chunk: aim at ~4 waves of 512 threads per SM so that small batches still fill the machine
+    uint32_t chunk_log = 3;
+    { const uint64_t target_units = (uint64_t)tb_tune("TB_MSM_UNITS_PER_SM", 2048) * (uint64_t)ctx->sm_count;
+      while ((1u << chunk_log) < (uint32_t)MSM_CHUNK_MAX && (max_entries >> chunk_log) > target_units) ++chunk_log; }
+    const uint64_t max_units = nb_total64 + (max_entries >> chunk_log) + 1;
+    const uint64_t max_heavy = (max_entries >> chunk_log) / MSM_HEAVY_UNITS + 1;
+    // three disjoint classes of buckets: <= 4 * lanes units (a group of `lanes` threads), <= 1024 units (one warp), more (one
+    // CTA each).  lanes: as wide as keeps ~4 warps per SM sub-partition busy, no wider than the average bucket needs.
+    uint32_t lpb_log = 0;
+    { const uint64_t avg_units = ((max_entries >> chunk_log) + nb_total64 - 1) / nb_total64;
+      const uint64_t warps_target = (uint64_t)tb_tune("TB_MSM_SUB_WARPS_PER_SM", 16) * (uint64_t)ctx->sm_count;
+      while (lpb_log < 5 && ((nb_total64 << (lpb_log + 1)) >> 5) <= warps_target && (1ull << lpb_log) < avg_units) ++lpb_log; }
+    const uint32_t sub_units = 4u << lpb_log;
+    uint64_t max_mid = (max_entries >> chunk_log) / sub_units + 1;   // buckets with more than sub_units * chunk entries
+    if (max_mid > nb_total64) max_mid = nb_total64;
+    DevBuf<uint32_t> unit_count(ctx, nb_total), unit_off(ctx, nb_total + 1), mid(ctx, max_mid), heavy(ctx, max_heavy), n_lists(ctx, 2);
+    n_lists.zero();
+    msm_units_kernel<<<(nb_total + 255) / 256, 256, 0, st>>>(offs.get(), nb_total, chunk_log, sub_units, unit_count.get(), mid.get(), heavy.get(), n_lists.get());
+    TB_LAUNCH_CHECK();
+    exclusive_scan_u32(ctx, unit_count.get(), unit_off.get(), nb_total);
+    DevBuf<Xyzz<B>> partial(ctx, max_units);
+    ctx->work[PC_MSM_ACCUM] += 10.5 * (double)max_entries * 0.97;                 // XYZZ mixed additions (upper bound: every digit non-zero)
+    ps.reset(); ps.reset(new ProfScope(ctx, PC_MSM_ACCUM));
+    { const unsigned ag = (unsigned)((max_units + 127) / 128);
+      const int minb = tb_tune("TB_MSM_ACCUM_MINB", 4);
+      if (minb >= 6) msm_accum_kernel<B, 6><<<ag, 128, 0, st>>>(bases, base_bstride, (uint32_t)wsep * NB, offs.get(), unit_off.get(), nb_total, 1u << chunk_log, entries.get(), partial.get());
+      else if (minb == 5) msm_accum_kernel<B, 5><<<ag, 128, 0, st>>>(bases, base_bstride, (uint32_t)wsep * NB, offs.get(), unit_off.get(), nb_total, 1u << chunk_log, entries.get(), partial.get());
+      else msm_accum_kernel<B, 4><<<ag, 128, 0, st>>>(bases, base_bstride, (uint32_t)wsep * NB, offs.get(), unit_off.get(), nb_total, 1u << chunk_log, entries.get(), partial.get()); }
+    TB_LAUNCH_CHECK();
+    ps.reset(); ps.reset(new ProfScope(ctx, PC_MSM_REDUCE));
+    msm_combine_sub_kernel<B><<<(unsigned)((((uint64_t)nb_total << lpb_log) + 127) / 128), 128, 0, st>>>(unit_off.get(), partial.get(), nb_total, lpb_log,
+                                                                                                        buckets.get());
+    { uint64_t g = (max_mid + 7) / 8, cap = 4ull * (uint64_t)ctx->sm_count;   // e.g. a witness column that is mostly small values
+      msm_combine_kernel<B><<<(unsigned)(g < cap ? g : cap), 256, 0, st>>>(mid.get(), n_lists.get(), unit_off.get(), partial.get(), buckets.get()); }
+    if ((max_entries >> chunk_log) > MSM_HEAVY_UNITS)  // e.g. the top window of a variable-base MSM, or a witness column that is mostly ones
+      msm_combine_heavy_kernel<B><<<(unsigned)(max_heavy < 296 ? max_heavy : 296), 256, 0, st>>>(heavy.get(), n_lists.get() + 1, unit_off.get(), partial.get(), buckets.get());
+    TB_LAUNCH_CHECK();
+    ps.reset();
+  }
+  ps.reset(new ProfScope(ctx, PC_MSM_REDUCE));
 
   const int seg_t = tb_tune("TB_MSM_SEG", MSM_SEG);
   const int seg = NB < seg_t ? NB : seg_t;
@@ -406,8 +419,7 @@ void msm_run(Ctx* ctx, const S* scalars, long long scalar_bstride, const Aff<B>*
     TB_LAUNCH_CHECK();
     const size_t smem = (size_t)threads * sizeof(Xyzz<B>);
     if (smem > 48 * 1024) {
-      static bool attr[2] = {false, false};
-      if (!attr[B::params_id()]) { TB_CUDA(cudaFuncSetAttribute(msm_weighted_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024)); attr[B::params_id()] = true; }
+      ctx->opt_in_smem(msm_weighted_kernel<B>, 128 * 1024);
     }
     msm_weighted_kernel<B><<<groups, threads, smem, st>>>(lines.get(), s_log, h_log, out, aff_out);
     TB_LAUNCH_CHECK();

@@ -130,6 +130,10 @@ void ntt_run(Ctx* ctx, int logn, bool inverse, const F* in, F* out, F* scratch, 
   TB_REQUIRE(logn >= 1 && logn <= TW_LOG, "NTT size out of range");
   TB_REQUIRE(batch >= 1 && batch <= 65535 && batch2 >= 1 && batch2 <= 65535, "NTT batch out of range");
   ProfScope prof_scope(ctx, PC_NTT);
+  { const double elems = (double)batch * batch2 * (double)(1ull << logn);
+    const double hook = (pre ? (pre->use_zeta ? 0.67 : 0.0) + (pre->k ? 1.0 : 0.0) + (pre->use_const ? 1.0 : 0.0) : 0.0) +
+                        ((post || inverse) ? 1.0 + (post && post->k ? 1.0 : 0.0) + (post && post->use_zeta ? 0.67 : 0.0) : 0.0);
+    ctx->work[PC_NTT] += elems * (0.5 * logn + hook + (logn > 10 ? 1.0 : 0.0)); }   // butterflies + hooks + inter-pass twiddles
   static bool attr_set[2] = {false, false};
   if (!attr_set[F::params_id()]) {
     TB_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));

@@ -62,13 +62,38 @@ static Circuit* circuit_load(Ctx* ctx, const Srs* srs, const tb_cs_desc* cs, con
   C.nconsts = cs->num_constants;
   C.consts_bytes.assign(cs->constants, cs->constants + 32 * (size_t)cs->num_constants);
   for (uint32_t l = 0; l < C.L; ++l) {
+    TB_REQUIRE(cs->lookups && cs->lookups[l].num_exprs >= 1 && cs->lookups[l].input_roots && cs->lookups[l].table_roots, "a lookup needs at least one expression pair");
     C.lk_in.emplace_back(cs->lookups[l].input_roots, cs->lookups[l].input_roots + cs->lookups[l].num_exprs);
     C.lk_tab.emplace_back(cs->lookups[l].table_roots, cs->lookups[l].table_roots + cs->lookups[l].num_exprs);
   }
   for (auto& q : C.aq) TB_REQUIRE(q.column < C.na, "advice query column out of range");
   for (auto& q : C.fq) TB_REQUIRE(q.column < C.nf, "fixed query column out of range");
   for (auto& q : C.iq) TB_REQUIRE(q.column < C.ni, "instance query column out of range");
-  for (auto& nd : C.nodes) TB_REQUIRE(nd.op <= TB_EX_SCALE, "bad expression node");
+  // the description comes across the ABI: reject anything that would make the expression compiler recurse without end or a
+  // kernel index out of bounds (forward references, cycles, stray constant / query / column indices)
+  for (size_t i = 0; i < C.nodes.size(); ++i) {
+    const tb_expr_node& nd = C.nodes[i];
+    TB_REQUIRE(nd.op <= TB_EX_SCALE, "bad expression node");
+    switch (nd.op) {
+      case TB_EX_CONST: TB_REQUIRE(nd.a < cs->num_constants, "expression constant index out of range"); break;
+      case TB_EX_ADVICE: TB_REQUIRE(nd.a < cs->num_advice_queries, "expression advice query index out of range"); break;
+      case TB_EX_FIXED: TB_REQUIRE(nd.a < cs->num_fixed_queries, "expression fixed query index out of range"); break;
+      case TB_EX_INSTANCE: TB_REQUIRE(nd.a < cs->num_instance_queries, "expression instance query index out of range"); break;
+      case TB_EX_NEG: TB_REQUIRE(nd.a < i, "expression nodes must be in topological order"); break;
+      case TB_EX_SCALE: TB_REQUIRE(nd.a < i && nd.b < cs->num_constants, "bad SCALE node"); break;
+      default: TB_REQUIRE(nd.a < i && nd.b < i, "expression nodes must be in topological order"); break;
+    }
+  }
+  for (uint32_t r : C.roots) TB_REQUIRE(r < C.nodes.size(), "constraint root out of range");
+  for (uint32_t l = 0; l < C.L; ++l) {
+    for (uint32_t r : C.lk_in[l]) TB_REQUIRE(r < C.nodes.size(), "lookup input root out of range");
+    for (uint32_t r : C.lk_tab[l]) TB_REQUIRE(r < C.nodes.size(), "lookup table root out of range");
+  }
+  for (auto& pc : C.perm) {
+    TB_REQUIRE(pc.kind <= TB_COL_INSTANCE, "permutation column kind out of range");
+    TB_REQUIRE(pc.index < (pc.kind == TB_COL_ADVICE ? C.na : pc.kind == TB_COL_FIXED ? C.nf : C.ni), "permutation column index out of range");
+  }
+  TB_REQUIRE(cs->blinding_factors >= 1 && cs->num_advice >= 1, "unsupported constraint system shape");
   memcpy(C.vk_repr.l, cs->vk_transcript_repr, 32);
 
   C.delta = delta_const<Fp>(); C.zeta = zeta_const<Fp>(); C.omega = omega_k<Fp>((int)C.k);
@@ -254,15 +279,27 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   cudaStream_t st = ctx->stream;
   size_t inst_total = 0;
   for (int c = 0; c < ni; ++c) { TB_REQUIRE(instance_len[c] <= C.usable, "InstanceTooLarge"); inst_total += instance_len[c]; }
-  WsAlloc ws{ctx, C.ws[B]};
-  std::vector<void*>& tables = C.cached_tables[B];
+  ProveWs& pws = C.workspace(ctx, B);
+  struct BusyGuard { std::atomic<int>& f; bool ok; explicit BusyGuard(std::atomic<int>& x) : f(x), ok(x.exchange(1) == 0) {} ~BusyGuard() { if (ok) f.store(0); } } guard(pws.busy);
+  TB_REQUIRE(guard.ok, "this proving key / context / batch size is already proving on another thread (a tb_ctx is bound to one thread)");
+  WsAlloc ws{ctx, pws.blocks};
+  std::vector<void*>& tables = pws.tables;
   size_t table_cur = 0;
-  // uploads a small host table once per (circuit, B); later calls reuse the device copy (contents are identical)
+  // uploads a small host table once per (circuit, context, B); later calls reuse the device copy.  The contents are compared with
+  // what was uploaded (they change only when a TB_* tuning knob changes between calls) and refreshed in stream order if they differ.
   auto cached_upload = [&](const void* host, size_t bytes) -> void* {
+    const uint8_t* hb = static_cast<const uint8_t*>(host);
     if (table_cur == tables.size()) {
       void* d = nullptr; TB_CUDA(cudaMalloc(&d, std::max<size_t>(16, bytes)));
       TB_CUDA(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
-      tables.push_back(d);
+      tables.push_back(d); pws.table_bytes.emplace_back(hb, hb + bytes);
+    } else {
+      std::vector<uint8_t>& old = pws.table_bytes[table_cur];
+      if (old.size() != bytes || memcmp(old.data(), host, bytes) != 0) {
+        if (old.size() < bytes) { cudaFree(tables[table_cur]); TB_CUDA(cudaMalloc(&tables[table_cur], bytes)); }
+        old.assign(hb, hb + bytes);
+        TB_CUDA(cudaMemcpyAsync(tables[table_cur], old.data(), bytes, cudaMemcpyHostToDevice, st));
+      }
     }
     return tables[table_cur++];
   };
@@ -279,6 +316,7 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   const int V_S_AT = va.one(), V_V = va.one(), V_LR = va.one(), V_RR = va.one(), V_VL = va.one(), V_VR = va.one();
   const int V_U = va.one(), V_UINV = va.one(), V_T0 = va.one(), V_C = va.one();
   const int V_YPOW = va.one(Q_MAX_PARTS);
+  const int V_YGRP = va.one(Q_MAX_GROUP + 1);   // y^i for the selector groups of the gate programs
   const int NV = va.next;
   WBuf<Fp> vars = ws.buf<Fp>((size_t)B * NV);
   vars.zero();
@@ -298,7 +336,7 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   WBuf<Fp> polys = ws.buf<Fp>((size_t)B * NC * n), cosets = ws.buf<Fp>((size_t)B * NC * n);
   WBuf<Aff<Fq>> pts = ws.buf<Aff<Fq>>((size_t)B * std::max({na + ni, 2 * L1, ns1 + L1, (int)C.pieces, 2}));
   WBuf<Fp> blinds = ws.buf<Fp>((size_t)B * std::max({na + ni, 2 * L1, ns1 + L1, (int)C.pieces, 4}));
-  WBuf<uint32_t> derr = ws.buf<uint32_t>(1); derr.zero();
+  WBuf<uint32_t> derr = ws.buf<uint32_t>((size_t)B * L1); derr.zero();   // one flag per (proof, lookup)
 
   // ---- instance + advice columns (commit_lagrange): one batched fixed-base MSM call for both
   // (the vanishing argument's random polynomial is committed over `g`, a different table: separate call)
@@ -341,7 +379,7 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   WBuf<Fp> lptab; lptab.p = lperm.get() + (size_t)B * L * n; lptab.n = (size_t)B * L1 * n; lptab.ctx = ctx;   // adjacent: one commitment call
   Fp* const lpin_polys = polys.get() + (size_t)O_LPIN * n; Fp* const lptab_polys = polys.get() + (size_t)O_LPTAB * n;
   QData qd; memset(&qd, 0, sizeof(qd));
-  qd.aq = C.d_aq; qd.fq = C.d_fq; qd.iq = C.d_iq; qd.consts = C.consts; qd.chal = vars.get(); qd.chal_stride = NV; qd.y_slot = V_Y; qd.theta_slot = V_THETA;
+  qd.consts = C.consts; qd.chal = vars.get(); qd.chal_stride = NV; qd.y_slot = V_Y; qd.theta_slot = V_THETA; qd.ygrp_slot = V_YGRP;
   qd.n = (int)n; qd.lk_pstride = (long long)L1 * nn;
   if (L) {
     qd.adv = adv_vals.get(); qd.adv_pstride = (long long)na * nn; qd.inst = inst_vals.get(); qd.inst_pstride = (long long)ni1 * nn;
@@ -434,7 +472,10 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   int gparts = tb_tune("TB_Q_PARTS", 8);
   while (gparts > 1 && C.gate_parts.at(gparts).size() < (size_t)gparts) gparts /= 2;
   const std::vector<QProgram>& gprogs = C.gate_parts.at(gparts); const std::vector<int>& gcounts = C.gate_part_counts.at(gparts);
-  { Prog p; for (size_t i = 1; i < gprogs.size(); ++i) p.op(S_POWI, V_YPOW + (int)i, V_Y, 0, (uint32_t)gcounts[i]); run_prog(p); }
+  { Prog p; for (size_t i = 1; i < gprogs.size(); ++i) p.op(S_POWI, V_YPOW + (int)i, V_Y, 0, (uint32_t)gcounts[i]);
+    p.op(S_COPY, V_YGRP + 1, V_Y);
+    for (int i = 2; i <= Q_MAX_GROUP; ++i) p.op(S_MUL, V_YGRP + i, V_YGRP + i - 1, V_Y);
+    run_prog(p); }
   WBuf<Fp> hext = ws.buf<Fp>((size_t)B * R * n), hcoef = ws.buf<Fp>((size_t)B * C.pieces * n);
   { WBuf<Fp> c_lkA = ws.buf<Fp>((size_t)B * L1 * n), c_lkS = ws.buf<Fp>((size_t)B * L1 * n), gate = ws.buf<Fp>((size_t)Q_MAX_PARTS * B * n), V = ws.buf<Fp>((size_t)B * R * n);
     Fp* const c_adv = cosets.get() + (size_t)O_ADV * n; Fp* const c_inst = cosets.get() + (size_t)O_INST * n; Fp* const c_pz = cosets.get() + (size_t)O_PZ * n;
@@ -605,12 +646,15 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
 
   // ---- download (the only host synchronisation of the call)
   std::vector<TrState> hst(B);
-  uint32_t herr = 0;
+  std::vector<uint32_t> herr((size_t)B * L1, 0);
   TB_CUDA(cudaMemcpyAsync(hst.data(), tr.states.get(), (size_t)B * sizeof(TrState), cudaMemcpyDeviceToHost, st));
-  TB_CUDA(cudaMemcpyAsync(&herr, derr.get(), 4, cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(herr.data(), derr.get(), herr.size() * 4, cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaMemcpy2DAsync(proofs_out, proof_stride, tr.proofs.get(), C.proof_len, C.proof_len, B, cudaMemcpyDeviceToHost, st));
   ctx->sync();
-  if (herr) throw ConstraintError("lookup input not contained in the table (ConstraintSystemFailure)");
+  for (int b = 0; b < B; ++b) for (int l = 0; l < L; ++l)
+    if (herr[(size_t)b * L + l])
+      throw ConstraintError("proof " + std::to_string(b) + " of the batch (index " + std::to_string(proof0 + (uint32_t)b) + "): an input of lookup " + std::to_string(l) +
+                            " is not contained in its table (ConstraintSystemFailure)");
   for (int b = 0; b < B; ++b) {
     if (hst[b].error & TR_ERR_INFINITY) throw std::runtime_error("cannot write points at infinity to the transcript");
     if (hst[b].error || hst[b].proof_len != C.proof_len) throw std::runtime_error("internal error: proof length mismatch");

@@ -12,10 +12,11 @@ void lookup_arrange(Ctx* c, const Fp* sortedA, const Fp* sortedT, Fp* scratch, F
 // ---------------------------------------------------------------- quotient.cu
 // Row-parallel expression interpreter.  Temporaries live in a shared-memory register file laid
 // out [reg][thread] as two 16-byte halves; leaves (column queries, constants) are read straight from global memory.
-enum QOp { Q_MOV = 0, Q_NEG, Q_ADD, Q_SUB, Q_MUL, Q_FOLD_Y, Q_LK_BEGIN, Q_FOLD_A, Q_FOLD_S, Q_LK_STORE };
+enum QOp { Q_MOV = 0, Q_NEG, Q_ADD, Q_SUB, Q_MUL, Q_FOLD_Y, Q_LK_BEGIN, Q_FOLD_A, Q_FOLD_S, Q_LK_STORE, Q_GBEGIN, Q_GFOLD, Q_GEND };
+constexpr int Q_MAX_GROUP = 32;   // longest run of constraints folded as one selector group (needs y^2 .. y^Q_MAX_GROUP per proof)
 enum QKind { K_REG = 0, K_ADV, K_FIX, K_INST, K_CONST };
-struct QInstr { uint32_t w0; uint32_t a, b; };  // w0 = op | dst << 8 | akind << 16 | bkind << 24
-inline QInstr q_make(int op, int dst, int ak, uint32_t a, int bk, uint32_t b) { QInstr i; i.w0 = op | (dst << 8) | (ak << 16) | (bk << 24); i.a = a; i.b = b; return i; }
+struct alignas(16) QInstr { uint32_t w0; uint32_t a, b, pad; };  // w0 = op | dst << 8 | akind << 16 | bkind << 24 (one 128-bit load)
+inline QInstr q_make(int op, int dst, int ak, uint32_t a, int bk, uint32_t b) { QInstr i; i.w0 = op | (dst << 8) | (ak << 16) | (bk << 24); i.a = a; i.b = b; i.pad = 0; return i; }
 
 struct QProgram {           // compiled once per circuit (host), resident on the device
   std::vector<QInstr> host; int nregs = 0;
@@ -35,9 +36,8 @@ struct QData {
   const Fp* adv; long long adv_pstride;     // [B][num_advice][n]
   const Fp* inst; long long inst_pstride;   // [B][num_instance][n]
   const Fp* fix; int R; int k1;             // [num_fixed][R][n]  (R = 1: Lagrange values)
-  const int2* aq; const int2* fq; const int2* iq;   // (column, rotation) per query
   const Fp* consts;                         // Montgomery
-  const Fp* chal; long long chal_stride; int y_slot, theta_slot;
+  const Fp* chal; long long chal_stride; int y_slot, theta_slot, ygrp_slot;   // chal[ygrp_slot + i] = y^i, 2 <= i <= Q_MAX_GROUP
   Fp* gate_out; long long gate_pstride;     // [B][n]
   Fp* lkA; Fp* lkS; long long lk_pstride;   // [B][L][n]
   int n;

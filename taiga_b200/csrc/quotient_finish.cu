@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(128) q_finish_kernel(QFinish f) {
 
 void q_finish(Ctx* c, const QFinish& f, int B) {
   ProfScope prof_scope(c, PC_QUOT_FINISH);
+  c->work[PC_QUOT_FINISH] += (double)f.n * B * (3.0 * f.P + 6.0 * f.nsets + 16.0 * f.L + 2.0 * f.nparts + 8.0);   // permutation products, lookup terms, y folds
   q_finish_kernel<<<dim3((f.n + 127) / 128, B), 128, 0, c->stream>>>(f);
   TB_LAUNCH_CHECK(); c->launches++;
 }

@@ -169,6 +169,7 @@ static void verify_batch(Ctx* ctx, const Circuit& C, int K, const uint8_t* insta
   size_t inst_total = 0; for (int c = 0; c < ni; ++c) inst_total += instance_len[c];
   for (int p = 0; p < K; ++p) ok_out[p] = 0;
   // ---- verifying-key commitments (computed once per circuit, cached)
+  std::unique_lock<std::mutex> vk_lock(C.mu);
   if (C.vk_fixed.size() != (size_t)nf || C.vk_sigma.size() != (size_t)P) {
     for (int which = 0; which < 2; ++which) {
       int cnt = which ? P : nf;
@@ -181,6 +182,7 @@ static void verify_batch(Ctx* ctx, const Circuit& C, int K, const uint8_t* insta
       pts.download(dst.data(), cnt); ctx->sync();
     }
   }
+  vk_lock.unlock();
   // ---- instance commitments for the whole batch: commit_lagrange(instance, Blind::default())
   std::vector<Aff<Fq>> inst_comm((size_t)K * std::max(1, ni), Aff<Fq>::inf());
   if (ni) {

@@ -41,6 +41,7 @@ _SIGS = {
     "tb_prof_category_name": (ctypes.c_char_p, [_i]),
     "tb_prof_enable": (_i, [_vp, _i]),
     "tb_prof_read": (_i, [_vp, _vp, _vp]),
+    "tb_prof_work": (_i, [_vp, _vp]),
     "tb_ntt": (_i, [_vp, _i, _u32, _i, _i, _u32, _vp, _vp]),
     "tb_msm": (_i, [_vp, _i, _sz, _u32, _vp, _vp, _u32, _vp]),
     "tb_dev_to_mont": (_i, [_vp, _i, _vp, _sz]),
@@ -142,6 +143,13 @@ class Context:
         cnt = np.zeros(n, np.uint64)
         self._check(self._lib.tb_prof_read(self._h, _ptr(ms), _ptr(cnt)))
         return {self._lib.tb_prof_category_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+    def work_read(self):
+        """{category: Montgomery multiplications executed since the last read} (the numerator of the integer-pipe roofline)."""
+        n = self._lib.tb_prof_categories()
+        mm = np.zeros(n, np.float64)
+        self._check(self._lib.tb_prof_work(self._h, _ptr(mm)))
+        return {self._lib.tb_prof_category_name(i).decode(): float(mm[i]) for i in range(n)}
 
     # ---- host-buffer primitives
     def ntt(self, field, data, inverse=False, coset=False, batch=1):

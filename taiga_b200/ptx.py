@@ -59,25 +59,29 @@ class ProverService:
         self.pk_c, self.pk_v = self.c_workers[0][1], self.v_workers[0][1]
         self.contexts = [w[0] for w in self.c_workers + self.v_workers]
 
-    def synthesize_ptx(self, n_ptx, wseed=0):
+    def synthesize_ptx(self, n_ptx, wseed=0, procs=None):
         """Witness tables for n_ptx partial transactions: dict of stacked numpy arrays (host)."""
-        cw = [self.kd_c.witness_arrays(self.make_c(wseed * 1000 + i)) for i in range(COMPLIANCE_PER_PTX * n_ptx)]
-        vw = [self.kd_v.witness_arrays(self.make_v(wseed * 1000 + 500 + i)) for i in range(VP_PER_PTX * n_ptx)]
+        jobs = [(True, wseed * 100000 + i) for i in range(COMPLIANCE_PER_PTX * n_ptx)] + \
+               [(False, wseed * 100000 + 50000 + i) for i in range(VP_PER_PTX * n_ptx)]
+        res = _synthesize_many(self, jobs, procs)
+        cw, vw = res[:COMPLIANCE_PER_PTX * n_ptx], res[COMPLIANCE_PER_PTX * n_ptx:]
         return {
             "c_adv": np.stack([w[0] for w in cw]), "c_inst": np.stack([w[1] for w in cw]), "c_len": cw[0][2],
             "v_adv": np.stack([w[0] for w in vw]), "v_inst": np.stack([w[1] for w in vw]), "v_len": vw[0][2],
         }
 
-    def build_ptx_batch(self, wit, seed, c_adv=None, v_adv=None, max_batch=64):
+    def build_ptx_batch(self, wit, seed, c_adv=None, v_adv=None, max_batch=64, workers_per_circuit=None):
         """ShieldedPartialTransaction::build for a batch: returns (compliance proofs, vp proofs) as lists of bytes.
-        c_adv / v_adv may override the advice buffers (e.g. pinned host or device-resident torch tensors)."""
+        c_adv / v_adv may override the advice buffers (e.g. pinned host or device-resident torch tensors).
+        workers_per_circuit limits how many of the service's (stream, key) pairs share the batch (large batches fill
+        the GPU from one stream per circuit; single partial transactions want two, to overlap their latency-bound phases)."""
         c_adv = wit["c_adv"] if c_adv is None else c_adv
         v_adv = wit["v_adv"] if v_adv is None else v_adv
         jobs = []   # (result slot, worker, first proof, last proof, ...)
         for kind, workers, adv, inst, lens, index0 in (("c", self.c_workers, c_adv, wit["c_inst"], wit["c_len"], 0),
                                                        ("v", self.v_workers, v_adv, wit["v_inst"], wit["v_len"], 1 << 20)):
             total = len(inst)
-            nw = min(len(workers), total)
+            nw = min(len(workers) if not workers_per_circuit else min(len(workers), workers_per_circuit), total)
             for w in range(nw):
                 lo, hi = total * w // nw, total * (w + 1) // nw
                 jobs.append((kind, lo, hi, workers[w], adv, inst, lens, index0))
@@ -122,6 +126,13 @@ class ProverService:
                 tot[k_] = (a[0] + v_[0], a[1] + v_[1])
         return tot
 
+    def work_read(self):
+        tot = {}
+        for c in self.contexts:
+            for k_, v_ in c.work_read().items():
+                tot[k_] = tot.get(k_, 0.0) + v_
+        return tot
+
     @staticmethod
     def _prove_range(pk, ctx, adv, inst, lens, seed, max_batch, index0, lo, hi):
         kd = pk.keydata
@@ -136,6 +147,32 @@ class ProverService:
                 chunk = adv.reshape(total, -1)[s:e]
             out += pk.prove_batch_raw(chunk, e - s, inst[s:e], lens, seed, index0 + s, ctx=ctx)
         return out
+
+
+_SYNTH_SVC = None
+
+
+def _synth_one(job):
+    comp, seed = job
+    svc = _SYNTH_SVC
+    return (svc.kd_c.witness_arrays(svc.make_c(seed)) if comp else svc.kd_v.witness_arrays(svc.make_v(seed)))
+
+
+def _synthesize_many(svc, jobs, procs=None):
+    """Host witness synthesis (the stand-in for the Rust `Circuit::synthesize`, compliance_circuit.rs:174-327) of many
+    proofs: forked worker processes, one witness per task."""
+    global _SYNTH_SVC
+    import multiprocessing as mp
+    import os
+    procs = procs or min(len(jobs), max(1, (os.cpu_count() or 2) - 2), 64)
+    _SYNTH_SVC = svc
+    try:
+        if procs <= 1 or len(jobs) <= 2:
+            return [_synth_one(j) for j in jobs]
+        with mp.get_context("fork").Pool(procs) as pool:
+            return pool.map(_synth_one, jobs, chunksize=1)
+    finally:
+        _SYNTH_SVC = None
 
 
 class _TensorSlice:

@@ -41,8 +41,9 @@ def test_field(shim):
             for b in rnd.sample(vals, 4) + edge[:4]:
                 assert fo(f, 0, a, b) == (a + b) % m and fo(f, 1, a, b) == (a - b) % m and fo(f, 2, a, b) == a * b % m
             assert fo(f, 4, a) == (-a) % m and fo(f, 5, a) == a * a % m
-        for a in vals[:12]:
-            assert fo(f, 3, a) == pow(a, m - 2, m)
+        # inversion (divsteps, field.cuh::inv): every edge value, small values, powers of two and many random ones
+        for a in vals + list(range(2, 40)) + [1 << i for i in range(1, 254, 7)] + [m - (1 << i) for i in range(1, 250, 11)] + [rnd.randrange(m) for _ in range(3000)]:
+            assert fo(f, 3, a) == pow(a, m - 2, m), hex(a)
 
 
 def test_curve(shim):
