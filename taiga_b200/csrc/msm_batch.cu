@@ -23,6 +23,7 @@
 //
 // Algorithmic bytes: 64*N*W (table) + 32*N*K.  The rounds deliberately spend HBM bytes (each round writes its items) to
 // save integer instructions; DESIGN.md section 4 has the accounting.
+#define TB_NOINLINE_MUL 0   // every loop of this file is rolled (small code): inline multiplies keep live values in registers instead of spilling them around calls
 #include <cuda.h>
 #include <algorithm>
 #include <memory>
@@ -392,7 +393,7 @@ void msm_batch_buckets(Ctx* ctx, const S* scalars, long long sstride, const Aff<
   TB_REQUIRE(((uintptr_t)scalars & 15) == 0 && (sstride * (long long)sizeof(S)) % 16 == 0, "scalar vectors must be 16-byte aligned for TMA");
   const long long cap0 = (long long)(N + n_extra) * W;
   std::vector<long long> cap(1, cap0);
-  const int R = tb_tune("TB_MSM_BA_ROUNDS", 11);
+  const int R = tb_tune("TB_MSM_BA_ROUNDS", 10);
   TB_REQUIRE(R >= 1 && R <= 20, "TB_MSM_BA_ROUNDS out of range");
   for (int r = 0; r < R; ++r) cap.push_back((cap.back() + NB + 1) / 2);
   const int Kc_max = tb_tune("TB_MSM_BA_CHUNK", 256);
