@@ -33,7 +33,7 @@
 namespace tb {
 
 constexpr int BA_THREADS = 256;
-constexpr int BA_M = 16;                        // pairs per thread
+constexpr int BA_M = 32;                        // default pairs per thread (TB_MSM_BA_M)
 constexpr int BA_PAIRS = BA_THREADS * BA_M;     // output items per CTA
 constexpr int BA_MAX_NB = 4096;
 constexpr int SORT_THREADS = 1024;
@@ -236,13 +236,13 @@ __global__ void __launch_bounds__(BA_THREADS) msm_ba_count_kernel(const uint32_t
 
 // ---- 2a. forward: prefix products of the denominators (to global memory), product tree of the CTA (to global memory)
 // A CTA owns BA_PAIRS consecutive output items of one MSM; thread t owns items Q0 + i * BA_THREADS + t.
-template <class B, bool FIRST>
+template <class B, bool FIRST, int M>
 __global__ void __launch_bounds__(BA_THREADS) msm_ba_fwd_kernel(const uint32_t* __restrict__ counts0, int NB, int round, const uint32_t* __restrict__ entries,
                                                                  const Aff<B>* __restrict__ table, const Aff<B>* __restrict__ items_in, long long cap_in, long long cap_out,
                                                                  B* __restrict__ pre, B* __restrict__ tree, uint32_t* __restrict__ meta, const uint32_t* __restrict__ n_items, int R) {
   extern __shared__ __align__(16) uint8_t ba_smem[];
   const int k = blockIdx.y, t = threadIdx.x;
-  const uint32_t Q0 = blockIdx.x * BA_PAIRS;
+  const uint32_t Q0 = blockIdx.x * (M * BA_THREADS);
   if (Q0 >= n_items[(long long)k * (R + 1) + round + 1]) return;   // nothing of this MSM left for this CTA (uniform over the CTA)
   RoundOffsets ro; ro.build(ba_smem, counts0 + (long long)k * NB, NB, round);
   PairLoader<B, FIRST> ld{entries + (FIRST ? (long long)k * cap_in : 0), table, items_in + (FIRST ? 0 : (long long)k * cap_in)};
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(BA_THREADS) msm_ba_fwd_kernel(const uint32_t* 
   uint32_t* meta_k = meta + (long long)k * cap_out;
   B acc = B::one();
 #pragma unroll 1
-  for (int i = 0; i < BA_M; ++i) {
+  for (int i = 0; i < M; ++i) {
     const uint32_t q = Q0 + (uint32_t)i * BA_THREADS + t;
     if (q >= ro.n_next) break;
     uint32_t in0; bool two; ro.locate(q, NB, in0, two);
@@ -288,14 +288,14 @@ __global__ void msm_ba_inv_kernel(B* __restrict__ tree, uint32_t n_trees) {
 }
 
 // ---- 2c. backward: push the inverted root down the tree, then walk every thread's pairs back and write the sums
-template <class B, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, 3) msm_ba_bwd_kernel(const uint32_t* __restrict__ counts0, int NB, int round, const uint32_t* __restrict__ entries,
+template <class B, bool FIRST, int M, int MINB>
+__global__ void __launch_bounds__(BA_THREADS, MINB) msm_ba_bwd_kernel(const uint32_t* __restrict__ counts0, int NB, int round, const uint32_t* __restrict__ entries,
                                                                  const Aff<B>* __restrict__ table, const Aff<B>* __restrict__ items_in, long long cap_in,
                                                                  Aff<B>* __restrict__ items_out, long long cap_out, const B* __restrict__ pre, const B* __restrict__ tree,
                                                                  const uint32_t* __restrict__ meta, const uint32_t* __restrict__ n_items, int R) {
   extern __shared__ __align__(16) uint8_t ba_smem[];
   const int k = blockIdx.y, t = threadIdx.x;
-  const uint32_t Q0 = blockIdx.x * BA_PAIRS;
+  const uint32_t Q0 = blockIdx.x * (M * BA_THREADS);
   const uint32_t n_next = n_items[(long long)k * (R + 1) + round + 1];
   if (Q0 >= n_next) return;
   B* nd = reinterpret_cast<B*>(ba_smem);   // [2 * BA_THREADS]
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(BA_THREADS, 3) msm_ba_bwd_kernel(const uint32_
   const B* pre_k = pre + (long long)k * cap_out;
   const uint32_t* meta_k = meta + (long long)k * cap_out;
   Aff<B>* out = items_out + (long long)k * cap_out;
-  int last = BA_M - 1;
+  int last = M - 1;
   while (last >= 0 && Q0 + (uint32_t)last * BA_THREADS + t >= n_next) --last;
 #pragma unroll 1
   for (int i = last; i >= 0; --i) {
@@ -378,6 +378,25 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+// one reduction round = forward, root inversion, backward; (pairs per thread, resident CTAs per SM) are tuning parameters
+template <class B, bool FIRST, int M, int MINB>
+static void launch_round_t(Ctx* ctx, dim3 grid, size_t fwd_smem, size_t bwd_smem, const uint32_t* counts, int NB, int r, const uint32_t* entries, const Aff<B>* table, const Aff<B>* in,
+                           long long cap_in, Aff<B>* out, long long cap_out, B* pre, B* tree, uint32_t* meta, const uint32_t* n_items, int R, uint32_t n_trees) {
+  cudaStream_t st = ctx->stream;
+  ctx->opt_in_smem(msm_ba_fwd_kernel<B, FIRST, M>, fwd_smem);
+  ctx->opt_in_smem(msm_ba_bwd_kernel<B, FIRST, M, MINB>, bwd_smem);
+  msm_ba_fwd_kernel<B, FIRST, M><<<grid, BA_THREADS, fwd_smem, st>>>(counts, NB, r, entries, table, in, cap_in, cap_out, pre, tree, meta, n_items, R);
+  msm_ba_inv_kernel<B><<<(n_trees + 63) / 64, 64, 0, st>>>(tree, n_trees);
+  msm_ba_bwd_kernel<B, FIRST, M, MINB><<<grid, BA_THREADS, bwd_smem, st>>>(counts, NB, r, entries, table, in, cap_in, out, cap_out, pre, tree, meta, n_items, R);
+}
+template <class B, typename... A> static void launch_round(Ctx* ctx, int M, int minb, bool first, A... a) {
+#define TB_LR(MM, NN) (first ? launch_round_t<B, true, MM, NN>(ctx, a...) : launch_round_t<B, false, MM, NN>(ctx, a...))
+  if (M == 8) { if (minb == 2) TB_LR(8, 2); else if (minb == 3) TB_LR(8, 3); else TB_LR(8, 4); }
+  else if (M == 32) { if (minb == 2) TB_LR(32, 2); else if (minb == 3) TB_LR(32, 3); else TB_LR(32, 4); }
+  else { if (minb == 2) TB_LR(16, 2); else if (minb == 3) TB_LR(16, 3); else TB_LR(16, 4); }
+#undef TB_LR
+}
+
 bool msm_batch_applicable(int N, int K, const MsmConfig& cfg, int c) {
   if (cfg.table_windows <= 0 || (1 << (c - 1)) > BA_MAX_NB || c < 6) return false;
   const long long min_terms = tb_tune("TB_MSM_BA_MIN_TERMS", 1 << 21);
@@ -396,7 +415,7 @@ void msm_batch_buckets(Ctx* ctx, const S* scalars, long long sstride, const Aff<
   const int R = tb_tune("TB_MSM_BA_ROUNDS", 10);
   TB_REQUIRE(R >= 1 && R <= 20, "TB_MSM_BA_ROUNDS out of range");
   for (int r = 0; r < R; ++r) cap.push_back((cap.back() + NB + 1) / 2);
-  const int Kc_max = tb_tune("TB_MSM_BA_CHUNK", 256);
+  const int Kc_max = tb_tune("TB_MSM_BA_CHUNK", 512);
   const int Kc = K < Kc_max ? K : Kc_max;
   DevBuf<uint32_t> counts(ctx, (size_t)Kc * NB), entries(ctx, (size_t)Kc * cap0);
   DevBuf<Aff<B>> itA(ctx, (size_t)Kc * cap[1]), itB(ctx, (size_t)Kc * (R > 1 ? cap[2] : 1));
@@ -406,10 +425,10 @@ void msm_batch_buckets(Ctx* ctx, const S* scalars, long long sstride, const Aff<
   const size_t fin_smem = (size_t)(NB + 4 + 32) * 4;
   ctx->opt_in_smem(msm_sort_kernel<S, 13>, sort_smem);
   ctx->opt_in_smem(msm_sort_kernel<S, 0>, sort_smem);
-  ctx->opt_in_smem(msm_ba_fwd_kernel<B, true>, fwd_smem); ctx->opt_in_smem(msm_ba_fwd_kernel<B, false>, fwd_smem);
-  ctx->opt_in_smem(msm_ba_bwd_kernel<B, true>, bwd_smem); ctx->opt_in_smem(msm_ba_bwd_kernel<B, false>, bwd_smem);
   ctx->opt_in_smem(msm_ba_finish_kernel<B>, fin_smem);
-  const unsigned ctas1 = (unsigned)((cap[1] + BA_PAIRS - 1) / BA_PAIRS);
+  const int Mv = tb_tune("TB_MSM_BA_M", 32) >= 32 ? 32 : tb_tune("TB_MSM_BA_M", 32) <= 8 ? 8 : 16, minb = tb_tune("TB_MSM_BA_MINB", 3) <= 2 ? 2 : tb_tune("TB_MSM_BA_MINB", 3) >= 4 ? 4 : 3;
+  const long long pairs_per_cta = (long long)Mv * BA_THREADS;
+  const unsigned ctas1 = (unsigned)((cap[1] + pairs_per_cta - 1) / pairs_per_cta);
   DevBuf<B> pre(ctx, (size_t)Kc * cap[1]), tree(ctx, (size_t)Kc * ctas1 * 2 * BA_THREADS);
   DevBuf<uint32_t> meta(ctx, (size_t)Kc * cap[1]), n_items(ctx, (size_t)Kc * (R + 1));
   for (int k0 = 0; k0 < K; k0 += Kc) {
@@ -432,14 +451,11 @@ void msm_batch_buckets(Ctx* ctx, const S* scalars, long long sstride, const Aff<
       for (int r = 0; r < R; ++r) {
         const Aff<B>* in = (r & 1) ? itA.get() : itB.get();   // round r reads what round r-1 wrote (r = 0 reads the entries)
         Aff<B>* out = (r & 1) ? itB.get() : itA.get();
-        const unsigned gx = (unsigned)((cap[r + 1] + BA_PAIRS - 1) / BA_PAIRS);
+        const unsigned gx = (unsigned)((cap[r + 1] + pairs_per_cta - 1) / pairs_per_cta);
         dim3 grid(gx, kc);
-        if (r == 0) msm_ba_fwd_kernel<B, true><<<grid, BA_THREADS, fwd_smem, st>>>(counts.get(), NB, 0, entries.get(), table, nullptr, cap0, cap[1], pre.get(), tree.get(), meta.get(), n_items.get(), R);
-        else msm_ba_fwd_kernel<B, false><<<grid, BA_THREADS, fwd_smem, st>>>(counts.get(), NB, r, nullptr, nullptr, in, cap[r], cap[r + 1], pre.get(), tree.get(), meta.get(), n_items.get(), R);
         const uint32_t n_trees = gx * (uint32_t)kc;
-        msm_ba_inv_kernel<B><<<(n_trees + 63) / 64, 64, 0, st>>>(tree.get(), n_trees);
-        if (r == 0) msm_ba_bwd_kernel<B, true><<<grid, BA_THREADS, bwd_smem, st>>>(counts.get(), NB, 0, entries.get(), table, nullptr, cap0, out, cap[1], pre.get(), tree.get(), meta.get(), n_items.get(), R);
-        else msm_ba_bwd_kernel<B, false><<<grid, BA_THREADS, bwd_smem, st>>>(counts.get(), NB, r, nullptr, nullptr, in, cap[r], out, cap[r + 1], pre.get(), tree.get(), meta.get(), n_items.get(), R);
+        launch_round<B>(ctx, Mv, minb, r == 0, grid, fwd_smem, bwd_smem, counts.get(), NB, r, entries.get(), table, in, r == 0 ? cap0 : cap[r], out, cap[r + 1], pre.get(), tree.get(),
+                        meta.get(), n_items.get(), R, n_trees);
         TB_LAUNCH_CHECK(); ctx->launches += 3;
       }
       const Aff<B>* last = (R & 1) ? itA.get() : itB.get();
