@@ -31,8 +31,11 @@ struct Circuit {
   Fp *fixed_vals = nullptr, *fixed_polys = nullptr, *fixed_cosets = nullptr, *sig_vals = nullptr, *sig_polys = nullptr, *sig_cosets = nullptr;
   Fp *l0 = nullptr, *l_last = nullptr, *l_blind = nullptr, *consts = nullptr, *wr_inv = nullptr;
   int2 *d_aq = nullptr, *d_fq = nullptr, *d_iq = nullptr, *d_perm = nullptr;
-  QProgram prog_gates, prog_lookups;
-  std::map<int, std::vector<QProgram>> gate_parts; std::map<int, std::vector<int>> gate_part_counts;   // keyed by number of parts
+  QProgram prog_lookups;
+  // gate programs keyed by number of parts: `gate_parts` holds the constraints evaluated on every sub-coset (all of them when the
+  // circuit is not split), `gate_parts_lo` the low-degree ones (degree <= R / 2) that are evaluated on every second sub-coset only
+  std::map<int, std::vector<QProgram>> gate_parts, gate_parts_lo;
+  bool split = false; uint32_t num_constraints = 0, t_pl = 0;   // t_pl: permutation + lookup terms folded after the gates
   std::vector<Fp> t_inv; Fp delta, zeta, omega, r_inv;
   Fp delta_c0[16];
   // evaluation / multiopen structure (host)
@@ -55,9 +58,10 @@ struct Circuit {
   ~Circuit() {
     for (auto& kv : ws) { for (auto& b : kv.second->blocks) cudaFree(b.p); for (void* p : kv.second->tables) cudaFree(p); }
     for (void* p : {(void*)fixed_vals, (void*)fixed_polys, (void*)fixed_cosets, (void*)sig_vals, (void*)sig_polys, (void*)sig_cosets, (void*)l0, (void*)l_last,
-                    (void*)l_blind, (void*)consts, (void*)wr_inv, (void*)d_aq, (void*)d_fq, (void*)d_iq, (void*)d_perm, (void*)prog_gates.dev, (void*)prog_lookups.dev})
+                    (void*)l_blind, (void*)consts, (void*)wr_inv, (void*)d_aq, (void*)d_fq, (void*)d_iq, (void*)d_perm, (void*)prog_lookups.dev})
       if (p) cudaFree(p);
     for (auto& kv : gate_parts) for (auto& qp : kv.second) if (qp.dev) cudaFree(qp.dev);
+    for (auto& kv : gate_parts_lo) for (auto& qp : kv.second) if (qp.dev) cudaFree(qp.dev);
   }
 };
 

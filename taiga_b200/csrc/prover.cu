@@ -142,12 +142,28 @@ static Circuit* circuit_load(Ctx* ctx, const Srs* srs, const tb_cs_desc* cs, con
 
   // expression programs (descriptor rebuilt from the deep copy so pointers stay valid)
   { tb_cs_desc d = *cs;
-    q_compile_gates(&d, &C.prog_gates);
-    for (int parts : {1, 2, 4, 8, 16}) q_compile_gates_split(&d, parts, &C.gate_parts[parts], &C.gate_part_counts[parts]);
+    C.num_constraints = cs->num_constraints;
+    C.t_pl = (C.nsets ? 2 + (C.nsets - 1) + C.nsets : 0) + 5 * C.L;
+    // Degree split: a constraint of degree <= R / 2 is a polynomial of fewer than (R / 2) * n coefficients, so the sum of all such
+    // constraints is fixed by its values on every second sub-coset; only the high-degree constraints (and the permutation /
+    // lookup terms) need all R sub-cosets.  Worth it when the low class carries a good part of the arithmetic.
+    std::vector<int> deg = q_constraint_degrees(&d);
+    std::vector<uint32_t> all, lo, hi;
+    for (uint32_t j = 0; j < cs->num_constraints; ++j) { all.push_back(j); ((C.R >= 4 && deg[j] <= C.R / 2) ? lo : hi).push_back(j); }
+    { std::vector<QProgram> t_all, t_lo;
+      q_compile_gates_split(&d, all, 1, &t_all); q_compile_gates_split(&d, lo, 1, &t_lo);
+      C.split = tb_tune("TB_Q_SPLIT", 1) != 0 && C.R >= 4 && !lo.empty() && !hi.empty() && t_lo[0].ninstr * 10 >= t_all[0].ninstr * 3;
+      if (getenv("TB_DEBUG")) fprintf(stderr, "[tb] circuit k=%u degree=%u: %u constraints, %zu of degree <= %d (%d of %d instructions): split %s\n", C.k, C.degree, cs->num_constraints,
+                                      lo.size(), C.R / 2, t_lo[0].ninstr, t_all[0].ninstr, C.split ? "on" : "off");
+      for (auto& qp : t_all) if (qp.dev) cudaFree(qp.dev);
+      for (auto& qp : t_lo) if (qp.dev) cudaFree(qp.dev); }
+    for (int parts : {1, 2, 4, 8, 16}) {
+      q_compile_gates_split(&d, C.split ? hi : all, parts, &C.gate_parts[parts]);
+      if (C.split) q_compile_gates_split(&d, lo, parts, &C.gate_parts_lo[parts]);
+    }
     if (getenv("TB_DEBUG")) {
-      fprintf(stderr, "[tb] circuit k=%u degree=%u: gates program %d instr / %d regs; lookups %d instr / %d regs\n", C.k, C.degree, C.prog_gates.ninstr,
-              C.prog_gates.nregs, C.prog_lookups.ninstr, C.prog_lookups.nregs);
-      for (auto& kv : C.gate_parts) { fprintf(stderr, "[tb]   %d parts:", kv.first); for (auto& qp : kv.second) fprintf(stderr, " %d/%d", qp.ninstr, qp.nregs); fprintf(stderr, "\n"); }
+      for (auto* m : {&C.gate_parts, &C.gate_parts_lo})
+        for (auto& kv : *m) { fprintf(stderr, "[tb]   %s %d parts:", m == &C.gate_parts ? "all/high" : "low", kv.first); for (auto& qp : kv.second) fprintf(stderr, " %d/%d", qp.ninstr, qp.nregs); fprintf(stderr, "\n"); }
     }
     q_compile_lookups(&d, &C.prog_lookups); }
 
@@ -315,8 +331,8 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   const int V_QBLIND = va.one(nps), V_P_BLIND = va.one(), V_S_BLIND = va.one(), V_F = va.one();
   const int V_S_AT = va.one(), V_V = va.one(), V_LR = va.one(), V_RR = va.one(), V_VL = va.one(), V_VR = va.one();
   const int V_U = va.one(), V_UINV = va.one(), V_T0 = va.one(), V_C = va.one();
-  const int V_YPOW = va.one(Q_MAX_PARTS);
-  const int V_YGRP = va.one(Q_MAX_GROUP + 1);   // y^i for the selector groups of the gate programs
+  const int YTAB = (int)(C.num_constraints + C.t_pl) + 2;
+  const int V_YTAB = va.one(YTAB);   // y^i, 0 <= i < YTAB: gap-aware folds of the gate programs and the weights that combine them
   const int NV = va.next;
   WBuf<Fp> vars = ws.buf<Fp>((size_t)B * NV);
   vars.zero();
@@ -379,7 +395,7 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   WBuf<Fp> lptab; lptab.p = lperm.get() + (size_t)B * L * n; lptab.n = (size_t)B * L1 * n; lptab.ctx = ctx;   // adjacent: one commitment call
   Fp* const lpin_polys = polys.get() + (size_t)O_LPIN * n; Fp* const lptab_polys = polys.get() + (size_t)O_LPTAB * n;
   QData qd; memset(&qd, 0, sizeof(qd));
-  qd.consts = C.consts; qd.chal = vars.get(); qd.chal_stride = NV; qd.y_slot = V_Y; qd.theta_slot = V_THETA; qd.ygrp_slot = V_YGRP;
+  qd.consts = C.consts; qd.chal = vars.get(); qd.chal_stride = NV; qd.y_slot = V_Y; qd.theta_slot = V_THETA; qd.ytab_slot = V_YTAB;
   qd.n = (int)n; qd.lk_pstride = (long long)L1 * nn;
   if (L) {
     qd.adv = adv_vals.get(); qd.adv_pstride = (long long)na * nn; qd.inst = inst_vals.get(); qd.inst_pstride = (long long)ni1 * nn;
@@ -470,26 +486,64 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   // fewer live temporaries per part = smaller shared-memory register file = higher occupancy (ncu: 6 warps/SM with one
   // 26-register program vs 20 warps/SM with eight <=11-register parts), for ~15% more instructions in total.
   int gparts = tb_tune("TB_Q_PARTS", 8);
-  while (gparts > 1 && C.gate_parts.at(gparts).size() < (size_t)gparts) gparts /= 2;
-  const std::vector<QProgram>& gprogs = C.gate_parts.at(gparts); const std::vector<int>& gcounts = C.gate_part_counts.at(gparts);
-  { Prog p; for (size_t i = 1; i < gprogs.size(); ++i) p.op(S_POWI, V_YPOW + (int)i, V_Y, 0, (uint32_t)gcounts[i]);
-    p.op(S_COPY, V_YGRP + 1, V_Y);
-    for (int i = 2; i <= Q_MAX_GROUP; ++i) p.op(S_MUL, V_YGRP + i, V_YGRP + i - 1, V_Y);
+  if (gparts != 1 && gparts != 2 && gparts != 4 && gparts != 8 && gparts != 16) gparts = 8;
+  const std::vector<QProgram>& gprogs = C.gate_parts.at(gparts);
+  const std::vector<QProgram>* lprogs = C.split ? &C.gate_parts_lo.at(gparts) : nullptr;
+  { Prog p; p.op(S_CONST, V_YTAB, 0, 0, 0); p.op(S_COPY, V_YTAB + 1, V_Y);
+    for (int i = 2; i < YTAB; ++i) p.op(S_MUL, V_YTAB + i, V_YTAB + i - 1, V_Y);
     run_prog(p); }
+  const int J = (int)C.num_constraints;
   WBuf<Fp> hext = ws.buf<Fp>((size_t)B * R * n), hcoef = ws.buf<Fp>((size_t)B * C.pieces * n);
   { WBuf<Fp> c_lkA = ws.buf<Fp>((size_t)B * L1 * n), c_lkS = ws.buf<Fp>((size_t)B * L1 * n), gate = ws.buf<Fp>((size_t)Q_MAX_PARTS * B * n), V = ws.buf<Fp>((size_t)B * R * n);
-    Fp* const c_adv = cosets.get() + (size_t)O_ADV * n; Fp* const c_inst = cosets.get() + (size_t)O_INST * n; Fp* const c_pz = cosets.get() + (size_t)O_PZ * n;
-    Fp* const c_lz = cosets.get() + (size_t)O_LZ * n; Fp* const c_lpin = cosets.get() + (size_t)O_LPIN * n; Fp* const c_lptab = cosets.get() + (size_t)O_LPTAB * n;
+    Fp* const c_adv0 = cosets.get() + (size_t)O_ADV * n;
+    const int Rlo = C.split ? R / 2 : 0;
+    // ---- low-degree constraints: every second sub-coset only.  Their sum H_lo is interpolated (Rlo * n coefficients) and divided by
+    // X^n - 1 in coefficient form, H_lo = q_lo (X^n - 1) + r_lo; q_lo goes straight into h, r_lo (n coefficients) joins the numerator
+    // of the high-degree part as one more polynomial on every sub-coset.  The column cosets computed here are kept for the second pass.
+    WBuf<Fp> keep, elo, vlo, clo, qlo, rlo_poly, rlo_coset;
+    if (C.split) {
+      keep = ws.buf<Fp>((size_t)Rlo * B * NC * n); elo = ws.buf<Fp>((size_t)B * Rlo * n); vlo = ws.buf<Fp>((size_t)B * Rlo * n); clo = ws.buf<Fp>((size_t)B * Rlo * n);
+      qlo = ws.buf<Fp>((size_t)B * Rlo * n); rlo_poly = ws.buf<Fp>((size_t)B * n); rlo_coset = ws.buf<Fp>((size_t)B * n);
+      int gexp[Q_MAX_PARTS] = {0};
+      for (size_t p = 0; p < lprogs->size(); ++p) gexp[p] = J - 1 - (*lprogs)[p].last + (int)C.t_pl;
+      for (int kq = 0; kq < Rlo; ++kq) {
+        const int k1 = 2 * kq;
+        Fp* ck = keep.get() + (size_t)kq * B * NC * n;
+        NttHook<Fp> h = coset_hook(C, k1, false);
+        ntt_run<Fp>(ctx, k, false, polys.get(), ck, scratch.get(), B * NC, nn, nn, &h, nullptr);
+        qd.adv = ck + (size_t)O_ADV * n; qd.adv_pstride = PS; qd.inst = ck + (size_t)O_INST * n; qd.inst_pstride = PS;
+        qd.fix = C.fixed_cosets; qd.R = R; qd.k1 = k1; qd.lkA = c_lkA.get(); qd.lkS = c_lkS.get();
+        qd.gate_out = gate.get(); qd.gate_pstride = nn;
+        q_run_parts(ctx, *lprogs, qd, (long long)B * nn, B);
+        q_combine(ctx, gate.get(), (int)lprogs->size(), (long long)B * nn, gexp, vars.get(), NV, V_YTAB, elo.get() + (size_t)kq * n, (long long)Rlo * nn, (int)n, B);
+      }
+      for (int kq = 0; kq < Rlo; ++kq) {   // interpolation on the coset zeta * <w_ext^2>: same two steps as extended_to_coeff, with R / 2 sub-cosets
+        NttHook<Fp> h = coset_hook(C, 2 * kq, true);
+        ntt_run<Fp>(ctx, k, true, elo.get() + (size_t)kq * n, vlo.get() + (size_t)kq * n, scratch.get(), B, (long long)Rlo * nn, (long long)Rlo * nn, nullptr, &h);
+      }
+      h_cross(ctx, vlo.get(), (long long)Rlo * nn, clo.get(), (long long)Rlo * nn, (int)n, Rlo, Rlo, C.wr_inv, 2, Fp::from_u32((uint32_t)Rlo).inv(), C.zeta.sqr(), B);
+      q_lo_split(ctx, clo.get(), (long long)Rlo * nn, Rlo, rlo_poly.get(), nn, qlo.get(), (long long)Rlo * nn, (int)n, B);
+    }
+    int gexp_hi[Q_MAX_PARTS] = {0};
+    for (size_t p = 0; p < gprogs.size(); ++p) gexp_hi[p] = J - 1 - gprogs[p].last;
     for (int k1 = 0; k1 < R; ++k1) {
       NttHook<Fp> h = coset_hook(C, k1, false);
-      ntt_run<Fp>(ctx, k, false, polys.get(), cosets.get(), scratch.get(), B * NC, nn, nn, &h, nullptr);
+      Fp* ck = cosets.get();
+      if (C.split && (k1 & 1) == 0) ck = keep.get() + (size_t)(k1 / 2) * B * NC * n;   // computed in the first pass
+      else ntt_run<Fp>(ctx, k, false, polys.get(), ck, scratch.get(), B * NC, nn, nn, &h, nullptr);
+      if (C.split) ntt_run<Fp>(ctx, k, false, rlo_poly.get(), rlo_coset.get(), scratch.get(), B, nn, nn, &h, nullptr);
+      Fp* const c_adv = ck + (size_t)O_ADV * n; Fp* const c_inst = ck + (size_t)O_INST * n; Fp* const c_pz = ck + (size_t)O_PZ * n;
+      Fp* const c_lz = ck + (size_t)O_LZ * n; Fp* const c_lpin = ck + (size_t)O_LPIN * n; Fp* const c_lptab = ck + (size_t)O_LPTAB * n;
+      (void)c_adv0;
       qd.adv = c_adv; qd.adv_pstride = PS; qd.inst = c_inst; qd.inst_pstride = PS;
       qd.fix = C.fixed_cosets; qd.R = R; qd.k1 = k1; qd.lkA = c_lkA.get(); qd.lkS = c_lkS.get();
       qd.gate_out = gate.get(); qd.gate_pstride = nn;
       q_run_parts(ctx, gprogs, qd, (long long)B * nn, B);
       if (L) { qd.gate_out = nullptr; q_run(ctx, C.prog_lookups, qd, B); }
       QFinish f; memset(&f, 0, sizeof(f));
-      f.gate = gate.get(); f.nparts = (int)gprogs.size(); f.gate_part_stride = (long long)B * nn; f.ypow_slot = V_YPOW; f.adv = c_adv; f.adv_pstride = PS; f.inst = c_inst; f.inst_pstride = PS;
+      f.gate = gate.get(); f.nparts = (int)gprogs.size(); f.gate_part_stride = (long long)B * nn; f.ytab_slot = V_YTAB; memcpy(f.gexp, gexp_hi, sizeof(gexp_hi));
+      f.rlo = C.split ? rlo_coset.get() : nullptr; f.rlo_pstride = nn;
+      f.adv = c_adv; f.adv_pstride = PS; f.inst = c_inst; f.inst_pstride = PS;
       f.fix = C.fixed_cosets; f.sig = C.sig_cosets; f.R = R; f.k1 = k1; f.l0 = C.l0; f.l_last = C.l_last; f.l_blind = C.l_blind;
       f.pz = c_pz; f.pz_pstride = PS; f.lz = c_lz; f.lpin = c_lpin; f.lptab = c_lptab; f.lk_pstride = PS; f.lkc_pstride = (long long)L1 * nn;
       f.lkA = c_lkA.get(); f.lkS = c_lkS.get(); f.perm_cols = C.d_perm; f.P = P; f.chunk = C.chunk; f.nsets = nsets; f.L = L; f.bf = bf;
@@ -503,7 +557,8 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
       NttHook<Fp> h = coset_hook(C, k1, true);
       ntt_run<Fp>(ctx, k, true, hext.get() + (size_t)k1 * n, V.get() + (size_t)k1 * n, scratch.get(), B, (long long)R * nn, (long long)R * nn, nullptr, &h);
     }
-    h_cross(ctx, V.get(), (long long)R * nn, hcoef.get(), (long long)C.pieces * nn, (int)n, R, (int)C.pieces, C.wr_inv, C.r_inv, C.zeta.sqr(), B);
+    h_cross(ctx, V.get(), (long long)R * nn, hcoef.get(), (long long)C.pieces * nn, (int)n, R, (int)C.pieces, C.wr_inv, 1, C.r_inv, C.zeta.sqr(), B);
+    if (C.split) q_add_blocks(ctx, hcoef.get(), (long long)C.pieces * nn, qlo.get(), (long long)Rlo * nn, Rlo - 1, (int)n, B);   // + H_lo div (X^n - 1)
   }
   prf_fill(ctx, seed, proof0, R_H_BLIND, 0, VP(V_H_BLINDS), NV, 1, (int)C.pieces, B);
   poly_copy(ctx, blinds.get(), C.pieces, VP(V_H_BLINDS), NV, C.pieces, B);

@@ -13,7 +13,6 @@ void lookup_arrange(Ctx* c, const Fp* sortedA, const Fp* sortedT, Fp* scratch, F
 // Row-parallel expression interpreter.  Temporaries live in a shared-memory register file laid
 // out [reg][thread] as two 16-byte halves; leaves (column queries, constants) are read straight from global memory.
 enum QOp { Q_MOV = 0, Q_NEG, Q_ADD, Q_SUB, Q_MUL, Q_FOLD_Y, Q_LK_BEGIN, Q_FOLD_A, Q_FOLD_S, Q_LK_STORE, Q_GBEGIN, Q_GFOLD, Q_GEND };
-constexpr int Q_MAX_GROUP = 32;   // longest run of constraints folded as one selector group (needs y^2 .. y^Q_MAX_GROUP per proof)
 enum QKind { K_REG = 0, K_ADV, K_FIX, K_INST, K_CONST };
 struct alignas(16) QInstr { uint32_t w0; uint32_t a, b, pad; };  // w0 = op | dst << 8 | akind << 16 | bkind << 24 (one 128-bit load)
 inline QInstr q_make(int op, int dst, int ak, uint32_t a, int bk, uint32_t b) { QInstr i; i.w0 = op | (dst << 8) | (ak << 16) | (bk << 24); i.a = a; i.b = b; i.pad = 0; return i; }
@@ -21,14 +20,17 @@ inline QInstr q_make(int op, int dst, int ak, uint32_t a, int bk, uint32_t b) { 
 struct QProgram {           // compiled once per circuit (host), resident on the device
   std::vector<QInstr> host; int nregs = 0;
   QInstr* dev = nullptr; int ninstr = 0;
+  int last = -1;            // index of the last constraint the program folds: its result is sum_j y^(last - j) e_j over its constraints
 };
 // Flattens the expression DAG reachable from `roots` into a register-allocated instruction list.
 // mode 0: gate constraints folded with y (Q_FOLD_Y per root);  mode 1: lookup compression (theta folds + stores)
-void q_compile_gates(const tb_cs_desc* cs, QProgram* out);
-// the constraint list split into `parts` contiguous groups of similar cost, one program each (row-parallel AND
-// constraint-parallel evaluation for small batches); counts[p] = number of constraints folded by part p
+// The (sorted) constraint subset `subset` split into `parts` groups of similar cost, one program each (row-parallel AND
+// constraint-parallel evaluation).  Folds are gap-aware: program p yields S_p = sum_{j in p} y^(last_p - j) e_j, so any
+// set of programs combines as sum_p y^(J - 1 - last_p) S_p, whatever subset of the J constraints each one holds.
 constexpr int Q_MAX_PARTS = 16;
-void q_compile_gates_split(const tb_cs_desc* cs, int parts, std::vector<QProgram>* out, std::vector<int>* counts);
+void q_compile_gates_split(const tb_cs_desc* cs, const std::vector<uint32_t>& subset, int parts, std::vector<QProgram>* out);
+// polynomial degree of every constraint (a column query counts 1): decides which sub-cosets a constraint must be evaluated on
+std::vector<int> q_constraint_degrees(const tb_cs_desc* cs);
 struct QPartList { const QInstr* prog[Q_MAX_PARTS]; int ninstr[Q_MAX_PARTS]; int nparts; long long part_stride; };
 void q_compile_lookups(const tb_cs_desc* cs, QProgram* out);
 
@@ -37,7 +39,7 @@ struct QData {
   const Fp* inst; long long inst_pstride;   // [B][num_instance][n]
   const Fp* fix; int R; int k1;             // [num_fixed][R][n]  (R = 1: Lagrange values)
   const Fp* consts;                         // Montgomery
-  const Fp* chal; long long chal_stride; int y_slot, theta_slot, ygrp_slot;   // chal[ygrp_slot + i] = y^i, 2 <= i <= Q_MAX_GROUP
+  const Fp* chal; long long chal_stride; int y_slot, theta_slot, ytab_slot;   // chal[ytab_slot + i] = y^i (0 <= i <= constraints + permutation / lookup terms)
   Fp* gate_out; long long gate_pstride;     // [B][n]
   Fp* lkA; Fp* lkS; long long lk_pstride;   // [B][L][n]
   int n;
@@ -48,7 +50,8 @@ void q_run_parts(Ctx* c, const std::vector<QProgram>& progs, QData d, long long 
 // permutation + lookup terms of the quotient, folded onto the gate accumulator, times 1/(X^n - 1) (constant per sub-coset)
 struct QFinish {
   const Fp* gate;          // [nparts][B][n] partial Horner sums of the gate constraints
-  int nparts; long long gate_part_stride; int ypow_slot;   // vars[ypow_slot + p] = y^(constraints in part p), p >= 1
+  int nparts; long long gate_part_stride; int ytab_slot; int gexp[Q_MAX_PARTS];   // numerator += chal[ytab_slot + gexp[p]] * gate[p]
+  const Fp* rlo; long long rlo_pstride;   // remainder of the low-degree numerator modulo X^n - 1 on this sub-coset (or null): added before the division
   const Fp* adv; long long adv_pstride; const Fp* inst; long long inst_pstride;   // sub-coset evaluations
   const Fp* fix; const Fp* sig; int R; int k1;      // [nf][R][n], [P][R][n]
   const Fp* l0; const Fp* l_last; const Fp* l_blind; // [R][n]
@@ -68,8 +71,16 @@ struct QFinish {
 void q_finish(Ctx* c, const QFinish& f, int B);
 
 // extended_to_coeff step B: size-R inverse transform across sub-cosets + zeta^-i, keeps `pieces` * n coefficients
-void h_cross(Ctx* c, const Fp* V, long long v_pstride, Fp* hcoef, long long h_pstride, int n, int R, int pieces, const Fp* d_wr_inv /* R */,
-             Fp r_inv, Fp zeta_inv, int B);
+void h_cross(Ctx* c, const Fp* V, long long v_pstride, Fp* hcoef, long long h_pstride, int n, int R, int pieces, const Fp* d_wr_inv /* R * wr_step */,
+             int wr_step, Fp r_inv, Fp zeta_inv, int B);
+// low-degree numerator (evaluated on every second sub-coset only):
+//   out[b][k][row] = sum_p chal[b][ytab_slot + gexp[p]] * gate[p][b][row]      (combination of the low programs on one sub-coset)
+void q_combine(Ctx* c, const Fp* gate, int nparts, long long part_stride, const int* gexp, const Fp* chal, long long chal_stride, int ytab_slot, Fp* out, long long out_pstride,
+               int n, int B);
+//   c[b][j][i], j < m: coefficients of H_lo.  r[b][i] = sum_j c[b][j][i] (= H_lo mod X^n - 1);  q[b][j][i] = sum_{t > j} c[b][t][i], j < m - 1 (= H_lo div X^n - 1)
+void q_lo_split(Ctx* c, const Fp* coef, long long c_pstride, int m, Fp* r, long long r_pstride, Fp* q, long long q_pstride, int n, int B);
+// h[b][j][i] += q[b][j][i], j < m
+void q_add_blocks(Ctx* c, Fp* h, long long h_pstride, const Fp* q, long long q_pstride, int m, int n, int B);
 
 // grand products (permutation / lookup)
 struct PermFrac {

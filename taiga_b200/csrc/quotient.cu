@@ -20,31 +20,33 @@ namespace {
 // A constraint list is compiled as a sequence of ITEMS.  Consecutive constraints of one gate usually share their selector
 // factor, root_j = S * X_j: since  acc <- acc * y + S * X_j  over such a run equals  acc * y^len + S * (Horner of the X_j in y),
 // the run is evaluated as a group with len + 1 multiplications instead of 2 * len (the result is the same field element, so
-// the proof bytes do not change).
-struct Item { bool group; uint32_t root; uint32_t S; std::vector<uint32_t> xs; };
+// the proof bytes do not change).  A program may hold any subset of the constraints: every fold multiplies by y^(gap to the
+// previous constraint of the program), read from a per-proof table of powers of y.
+struct Item { bool group; uint32_t root; uint32_t S; std::vector<uint32_t> xs; std::vector<uint32_t> pos; };   // pos: constraint index of every element
 
-std::vector<Item> build_items(const tb_cs_desc* cs, uint32_t r0, uint32_t r1) {
+std::vector<Item> build_items(const tb_cs_desc* cs, const std::vector<uint32_t>& idx) {
   std::vector<Item> items;
   auto factors = [&](uint32_t r, uint32_t* f) -> int { const tb_expr_node& nd = cs->nodes[r]; if (nd.op != TB_EX_MUL) return 0; f[0] = nd.a; f[1] = nd.b; return nd.a == nd.b ? 1 : 2; };
-  uint32_t i = r0;
-  while (i < r1) {
-    uint32_t f[2]; int nf = factors(cs->constraint_roots[i], f);
-    uint32_t j = i + 1;
-    while (nf && j < r1 && (int)(j - i) < Q_MAX_GROUP) {
-      uint32_t g[2]; int ng = factors(cs->constraint_roots[j], g);
+  size_t i = 0;
+  while (i < idx.size()) {
+    uint32_t f[2]; int nf = factors(cs->constraint_roots[idx[i]], f);
+    size_t j = i + 1;
+    while (nf && j < idx.size()) {
+      uint32_t g[2]; int ng = factors(cs->constraint_roots[idx[j]], g);
       uint32_t keep[2]; int nk = 0;
       for (int x = 0; x < nf; ++x) for (int y = 0; y < ng; ++y) if (f[x] == g[y]) { keep[nk++] = f[x]; break; }
       if (!nk) break;
       nf = nk; f[0] = keep[0]; if (nk > 1) f[1] = keep[1];
       ++j;
     }
+    Item it; it.S = 0; it.root = 0;
     if (j - i >= 2) {
-      Item it; it.group = true; it.root = 0; it.S = f[0];
-      for (uint32_t q = i; q < j; ++q) { const tb_expr_node& nd = cs->nodes[cs->constraint_roots[q]]; it.xs.push_back(nd.a == it.S ? nd.b : nd.a); }
-      items.push_back(it);
+      it.group = true; it.S = f[0];
+      for (size_t q = i; q < j; ++q) { const tb_expr_node& nd = cs->nodes[cs->constraint_roots[idx[q]]]; it.xs.push_back(nd.a == it.S ? nd.b : nd.a); it.pos.push_back(idx[q]); }
     } else {
-      Item it; it.group = false; it.root = cs->constraint_roots[i]; it.S = 0; items.push_back(it); j = i + 1;
+      it.group = false; it.root = cs->constraint_roots[idx[i]]; it.pos.push_back(idx[i]); j = i + 1;
     }
+    items.push_back(it);
     i = j;
   }
   return items;
@@ -120,27 +122,31 @@ struct Compiler {
     reg_of[node] = r;
     return {K_REG, (uint32_t)r, (int)node};
   }
-  // gate constraints [r0, r1) folded with y
-  void compile_constraints(uint32_t r0, uint32_t r1) {
-    std::vector<Item> items = build_items(cs, r0, r1);
+  // the constraints `idx` (ascending) folded with y; returns the index of the last one
+  int compile_constraints(const std::vector<uint32_t>& idx) {
+    std::vector<Item> items = build_items(cs, idx);
     std::vector<char> seen(cs->num_nodes, 0);
     for (auto& it : items) {
       if (!it.group) count(it.root, seen);
       else { count(it.S, seen); for (uint32_t x : it.xs) count(x, seen); }
     }
+    int prev = -1;
     for (auto& it : items) {
       if (!it.group) {
         Opnd o = emit(it.root);
-        code.push_back(q_make(Q_FOLD_Y, 0, o.kind, o.v, K_CONST, 0)); release(o);
+        code.push_back(q_make(Q_FOLD_Y, 0, o.kind, o.v, K_CONST, prev < 0 ? 1u : (uint32_t)((int)it.pos[0] - prev))); release(o);
+        prev = (int)it.pos[0];
         continue;
       }
       for (size_t j = 0; j < it.xs.size(); ++j) {
         Opnd o = emit(it.xs[j]);
-        code.push_back(q_make(j == 0 ? Q_GBEGIN : Q_GFOLD, 0, o.kind, o.v, K_CONST, 0)); release(o);
+        code.push_back(q_make(j == 0 ? Q_GBEGIN : Q_GFOLD, 0, o.kind, o.v, K_CONST, j == 0 ? 0u : it.pos[j] - it.pos[j - 1])); release(o);
       }
       Opnd os = emit(it.S);
-      code.push_back(q_make(Q_GEND, 0, os.kind, os.v, K_CONST, (uint32_t)it.xs.size())); release(os);
+      code.push_back(q_make(Q_GEND, 0, os.kind, os.v, K_CONST, prev < 0 ? 1u : (uint32_t)((int)it.pos.back() - prev))); release(os);
+      prev = (int)it.pos.back();
     }
+    return prev;
   }
 };
 void finish_program(Compiler& c, QProgram* out) {
@@ -155,35 +161,46 @@ void finish_program(Compiler& c, QProgram* out) {
 }
 }  // namespace
 
-void q_compile_gates(const tb_cs_desc* cs, QProgram* out) {
-  Compiler c(cs);
-  c.compile_constraints(0, cs->num_constraints);
-  finish_program(c, out);
+std::vector<int> q_constraint_degrees(const tb_cs_desc* cs) {
+  std::vector<int> deg(cs->num_nodes, -1);
+  for (uint32_t i = 0; i < cs->num_nodes; ++i) {   // nodes are in topological order (checked at circuit load)
+    const tb_expr_node& nd = cs->nodes[i];
+    switch (nd.op) {
+      case TB_EX_CONST: deg[i] = 0; break;
+      case TB_EX_ADVICE: case TB_EX_FIXED: case TB_EX_INSTANCE: deg[i] = 1; break;
+      case TB_EX_NEG: case TB_EX_SCALE: deg[i] = deg[nd.a]; break;
+      case TB_EX_ADD: deg[i] = deg[nd.a] > deg[nd.b] ? deg[nd.a] : deg[nd.b]; break;
+      default: deg[i] = deg[nd.a] + deg[nd.b]; break;
+    }
+  }
+  std::vector<int> out(cs->num_constraints);
+  for (uint32_t j = 0; j < cs->num_constraints; ++j) out[j] = deg[cs->constraint_roots[j]];
+  return out;
 }
 
-void q_compile_gates_split(const tb_cs_desc* cs, int parts, std::vector<QProgram>* out, std::vector<int>* counts) {
-  // cost of a root = instructions of its stand-alone program; contiguous groups with roughly equal cumulative cost
-  std::vector<size_t> cost(cs->num_constraints);
+void q_compile_gates_split(const tb_cs_desc* cs, const std::vector<uint32_t>& subset, int parts, std::vector<QProgram>* out) {
+  // cost of a root = instructions of its stand-alone program; contiguous (within the subset) groups with roughly equal cumulative cost
+  std::vector<size_t> cost(subset.size());
   size_t total = 0;
-  for (uint32_t i = 0; i < cs->num_constraints; ++i) {
+  for (size_t i = 0; i < subset.size(); ++i) {
     Compiler c(cs); std::vector<char> seen(cs->num_nodes, 0);
-    c.count(cs->constraint_roots[i], seen);
-    Compiler::Opnd o = c.emit(cs->constraint_roots[i]); (void)o;
+    c.count(cs->constraint_roots[subset[i]], seen);
+    Compiler::Opnd o = c.emit(cs->constraint_roots[subset[i]]); (void)o;
     cost[i] = c.code.size() + 1; total += cost[i];
   }
-  if (parts > (int)cs->num_constraints) parts = cs->num_constraints ? (int)cs->num_constraints : 1;
-  out->clear(); counts->clear();
-  uint32_t r0 = 0; size_t acc = 0;
+  if (parts > (int)subset.size()) parts = subset.empty() ? 1 : (int)subset.size();
+  out->clear();
+  size_t r0 = 0, acc = 0;
   for (int p = 0; p < parts; ++p) {
-    uint32_t r1 = r0;
-    size_t target = total * (p + 1) / parts;
-    while (r1 < cs->num_constraints && (acc < target || p == parts - 1)) acc += cost[r1++];
-    if (p == parts - 1) r1 = cs->num_constraints;
+    size_t r1 = r0;
+    const size_t target = total * (p + 1) / parts;
+    while (r1 < subset.size() && (acc < target || p == parts - 1)) acc += cost[r1++];
+    if (p == parts - 1) r1 = subset.size();
     Compiler c(cs);
-    c.compile_constraints(r0, r1);
+    const int last = c.compile_constraints(std::vector<uint32_t>(subset.begin() + r0, subset.begin() + r1));
     out->emplace_back();
     finish_program(c, &out->back());
-    counts->push_back((int)(r1 - r0));
+    out->back().last = last;
     r0 = r1;
   }
 }
@@ -256,12 +273,12 @@ __global__ void __launch_bounds__(128) q_interp_kernel(QPartList pl, int nregs, 
       case Q_ADD: r = fetch(ak, ia) + fetch(bk, ib); break;
       case Q_SUB: r = fetch(ak, ia) - fetch(bk, ib); break;
       case Q_MUL: r = fetch(ak, ia) * fetch(bk, ib); break;
-      case Q_FOLD_Y: r = lds(ACC) * chal[d.y_slot] + fetch(ak, ia); dst = ACC; break;
+      case Q_FOLD_Y: r = lds(ACC) * chal[d.ytab_slot + ib] + fetch(ak, ia); dst = ACC; break;   // acc = acc * y^gap + e
       case Q_FOLD_A: r = lds(ACC) * chal[d.theta_slot] + fetch(ak, ia); dst = ACC; break;
       case Q_FOLD_S: r = lds(G) * chal[d.theta_slot] + fetch(ak, ia); dst = G; break;
-      case Q_GFOLD: r = lds(G) * chal[d.y_slot] + fetch(ak, ia); dst = G; break;
+      case Q_GFOLD: r = lds(G) * chal[d.ytab_slot + ib] + fetch(ak, ia); dst = G; break;
       case Q_GBEGIN: r = fetch(ak, ia); dst = G; break;
-      case Q_GEND: r = lds(ACC) * chal[d.ygrp_slot + ib] + fetch(ak, ia) * lds(G); dst = ACC; break;   // acc = acc * y^len + S * g
+      case Q_GEND: r = lds(ACC) * chal[d.ytab_slot + ib] + fetch(ak, ia) * lds(G); dst = ACC; break;   // acc = acc * y^gap + S * g
       case Q_LK_BEGIN: r = Fp::zero(); sts(G, r); dst = ACC; break;
       case Q_LK_STORE: {
         const size_t o = (size_t)b * d.lk_pstride + (size_t)ia * d.n + row;

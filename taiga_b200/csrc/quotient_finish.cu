@@ -16,8 +16,8 @@ __global__ void __launch_bounds__(128) q_finish_kernel(QFinish f) {
   const Fp y = chal[f.y_slot], beta = chal[f.beta_slot], gamma = chal[f.gamma_slot];
   const Fp one = Fp::one();
   const size_t crow = (size_t)f.k1 * n + row;
-  Fp acc = ldg_fe(f.gate + (size_t)b * n + row);
-  for (int p = 1; p < f.nparts; ++p) acc = acc * chal[f.ypow_slot + p] + ldg_fe(f.gate + (size_t)p * f.gate_part_stride + (size_t)b * n + row);
+  Fp acc = Fp::zero();   // gate programs: sum_p y^(J - 1 - last_p) S_p
+  for (int p = 0; p < f.nparts; ++p) acc = acc + chal[f.ytab_slot + f.gexp[p]] * ldg_fe(f.gate + (size_t)p * f.gate_part_stride + (size_t)b * n + row);
   const Fp l0 = ldg_fe(f.l0 + crow), ll = ldg_fe(f.l_last + crow);
   const Fp active = one - (ll + ldg_fe(f.l_blind + crow));
   const Fp* adv = f.adv + (long long)b * f.adv_pstride;
@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(128) q_finish_kernel(QFinish f) {
     acc = acc * y + l0 * (ap - sp);
     acc = acc * y + (ap - sp) * (ap - apm) * active;
   }
+  if (f.rlo) acc = acc + ldg_fe(f.rlo + (long long)b * f.rlo_pstride + row);   // low-degree numerator modulo X^n - 1 (its quotient is added in coefficient form)
   st_fe(f.out + (long long)b * f.out_pstride + crow, acc * f.t_inv);
 }
 
@@ -69,7 +70,7 @@ void q_finish(Ctx* c, const QFinish& f, int B) {
 
 // ---------------------------------------------------------------- extended_to_coeff, step B
 __global__ void h_cross_kernel(const Fp* __restrict__ V, long long v_pstride, Fp* __restrict__ hcoef, long long h_pstride, int n, int R, int pieces,
-                               const Fp* __restrict__ wr_inv, Fp r_inv, Fp zeta_inv) {
+                               const Fp* __restrict__ wr_inv, int wr_step, Fp r_inv, Fp zeta_inv) {
   int i2 = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (i2 >= n) return;
   const Fp* v = V + (long long)b * v_pstride;
@@ -79,7 +80,7 @@ __global__ void h_cross_kernel(const Fp* __restrict__ V, long long v_pstride, Fp
     for (int k1 = 0; k1 < R; ++k1) {
       Fp x = ldg_fe(v + (size_t)k1 * n + i2);
       int e = (i1 * k1) & (R - 1);
-      acc = acc + (e ? x * ldg_fe(wr_inv + e) : x);
+      acc = acc + (e ? x * ldg_fe(wr_inv + e * wr_step) : x);
     }
     acc = acc * r_inv;
     uint32_t m3 = (uint32_t)((size_t)i1 * n + i2) % 3u;
@@ -87,9 +88,52 @@ __global__ void h_cross_kernel(const Fp* __restrict__ V, long long v_pstride, Fp
     st_fe(hcoef + (long long)b * h_pstride + (size_t)i1 * n + i2, acc);
   }
 }
-void h_cross(Ctx* c, const Fp* V, long long v_pstride, Fp* hcoef, long long h_pstride, int n, int R, int pieces, const Fp* d_wr_inv, Fp r_inv,
+void h_cross(Ctx* c, const Fp* V, long long v_pstride, Fp* hcoef, long long h_pstride, int n, int R, int pieces, const Fp* d_wr_inv, int wr_step, Fp r_inv,
              Fp zeta_inv, int B) {
-  h_cross_kernel<<<dim3((n + 127) / 128, B), 128, 0, c->stream>>>(V, v_pstride, hcoef, h_pstride, n, R, pieces, d_wr_inv, r_inv, zeta_inv);
+  h_cross_kernel<<<dim3((n + 127) / 128, B), 128, 0, c->stream>>>(V, v_pstride, hcoef, h_pstride, n, R, pieces, d_wr_inv, wr_step, r_inv, zeta_inv);
+  TB_LAUNCH_CHECK(); c->launches++;
+}
+
+// ---------------------------------------------------------------- low-degree part of the numerator (evaluated on every second sub-coset)
+struct QCombineArgs { int gexp[Q_MAX_PARTS]; };
+__global__ void q_combine_kernel(const Fp* __restrict__ gate, int nparts, long long part_stride, QCombineArgs a, const Fp* __restrict__ chal, long long chal_stride, int ytab_slot,
+                                 Fp* __restrict__ out, long long out_pstride, int n) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (row >= n) return;
+  const Fp* ch = chal + (long long)b * chal_stride;
+  Fp acc = Fp::zero();
+  for (int p = 0; p < nparts; ++p) acc = acc + ch[ytab_slot + a.gexp[p]] * ldg_fe(gate + (size_t)p * part_stride + (size_t)b * n + row);
+  st_fe(out + (long long)b * out_pstride + row, acc);
+}
+void q_combine(Ctx* c, const Fp* gate, int nparts, long long part_stride, const int* gexp, const Fp* chal, long long chal_stride, int ytab_slot, Fp* out, long long out_pstride,
+               int n, int B) {
+  ProfScope prof_scope(c, PC_QUOT_FINISH);
+  QCombineArgs a; for (int p = 0; p < Q_MAX_PARTS; ++p) a.gexp[p] = p < nparts ? gexp[p] : 0;
+  c->work[PC_QUOT_FINISH] += (double)n * B * nparts;
+  q_combine_kernel<<<dim3((n + 127) / 128, B), 128, 0, c->stream>>>(gate, nparts, part_stride, a, chal, chal_stride, ytab_slot, out, out_pstride, n);
+  TB_LAUNCH_CHECK(); c->launches++;
+}
+__global__ void q_lo_split_kernel(const Fp* __restrict__ coef, long long c_pstride, int m, Fp* __restrict__ r, long long r_pstride, Fp* __restrict__ q, long long q_pstride, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= n) return;
+  const Fp* cb = coef + (long long)b * c_pstride;
+  Fp run = Fp::zero();
+  for (int j = m - 1; j >= 1; --j) { run = run + ldg_fe(cb + (size_t)j * n + i); st_fe(q + (long long)b * q_pstride + (size_t)(j - 1) * n + i, run); }   // q_{j-1} = sum_{t >= j} c_t
+  st_fe(r + (long long)b * r_pstride + i, run + ldg_fe(cb + i));
+}
+void q_lo_split(Ctx* c, const Fp* coef, long long c_pstride, int m, Fp* r, long long r_pstride, Fp* q, long long q_pstride, int n, int B) {
+  q_lo_split_kernel<<<dim3((n + 127) / 128, B), 128, 0, c->stream>>>(coef, c_pstride, m, r, r_pstride, q, q_pstride, n);
+  TB_LAUNCH_CHECK(); c->launches++;
+}
+__global__ void q_add_blocks_kernel(Fp* __restrict__ h, long long h_pstride, const Fp* __restrict__ q, long long q_pstride, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= count) return;
+  Fp* hp = h + (long long)b * h_pstride + i;
+  st_fe(hp, ld_fe(hp) + ldg_fe(q + (long long)b * q_pstride + i));
+}
+void q_add_blocks(Ctx* c, Fp* h, long long h_pstride, const Fp* q, long long q_pstride, int m, int n, int B) {
+  const int count = m * n;
+  q_add_blocks_kernel<<<dim3((count + 255) / 256, B), 256, 0, c->stream>>>(h, h_pstride, q, q_pstride, count);
   TB_LAUNCH_CHECK(); c->launches++;
 }
 
