@@ -485,7 +485,7 @@ static void prove_batch(Ctx* ctx, const Circuit& C, int B, const uint8_t* advice
   // Constraint-parallel split of the gate program.  More parts = shorter per-thread chains (latency at small batches) AND
   // fewer live temporaries per part = smaller shared-memory register file = higher occupancy (ncu: 6 warps/SM with one
   // 26-register program vs 20 warps/SM with eight <=11-register parts), for ~15% more instructions in total.
-  int gparts = tb_tune("TB_Q_PARTS", 8);
+  int gparts = tb_tune("TB_Q_PARTS", B >= 8 ? 4 : 8);   // small batches: more, shorter programs (latency); large ones: less duplicated work
   if (gparts != 1 && gparts != 2 && gparts != 4 && gparts != 8 && gparts != 16) gparts = 8;
   const std::vector<QProgram>& gprogs = C.gate_parts.at(gparts);
   const std::vector<QProgram>* lprogs = C.split ? &C.gate_parts_lo.at(gparts) : nullptr;

@@ -42,6 +42,14 @@ def test_taiga_shape_proofs_bit_identical(gpu_ctx, gpu_srs, oracle_cpu, srs_fixt
     # tampering is rejected
     bad = bytearray(proofs[0]); bad[40] ^= 1
     assert okey.verify(wit[0][1], lens, bytes(bad)) != 0
+    # the independent pure-Python verifier (oracle/verifier_py.py, no code shared with the C++ restatement) accepts the GPU proof too
+    from oracle import verifier_py as vp
+    fc, sc = okey.commitments()
+    cols, off = [], 0
+    for l in lens:
+        cols.append([int.from_bytes(wit[0][1][32 * (off + i):32 * (off + i + 1)].tobytes(), "little") for i in range(int(l))])
+        off += int(l)
+    assert vp.verify(kd, srs_fixture, fc, sc, cols, proofs[0])
     # the product's own batched verifier gives the same verdicts
     assert pk.verify_batch(inst, lens, proofs) == [True, True]
     assert pk.verify_batch(inst, lens, [bytes(bad), ref]) == [False, True]
