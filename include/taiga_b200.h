@@ -120,7 +120,8 @@ tb_status tb_srs_commit(tb_ctx* ctx, const tb_srs* srs, int lagrange, uint32_t b
  *                  batch_invert_assigned; the last blinding_factors+1 rows are overwritten with blinding scalars)
  *   instance     : per proof the instance columns concatenated (sum(instance_len) elements); instance_len[num_instance]
  *   seed         : 32 bytes drawn from the caller's RNG (proof.rs:30); blinding scalars of proof i are derived from
- *                  (seed, first_proof_index + i), so results are reproducible for a given seed
+ *                  (seed, first_proof_index + i), so results are reproducible for a given seed.  A (seed, index) pair must never
+ *                  be reused for a different witness (it would reuse every blinding scalar): draw a fresh seed per call
  *   proofs_out   : n_proofs records of tb_pk_proof_len(pk) bytes at distance proof_stride
  * Errors: TB_ERR_CONSTRAINT mirrors plonk::Error::ConstraintSystemFailure (lookup input missing from its table),
  * TB_ERR_INVALID covers InstanceTooLarge and malformed arguments. */

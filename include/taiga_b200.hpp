@@ -172,6 +172,9 @@ class Proof {
   explicit Proof(std::vector<uint8_t> bytes) : bytes_(std::move(bytes)) {}
   const std::vector<uint8_t>& inner() const { return bytes_; }
 
+  // SECURITY: every blinding scalar of proof i is a PRF of (rng_seed, proof_index + i).  A (seed, index) pair must NEVER be used for
+  // two different witnesses -- reusing it reuses all blinding scalars and leaks witness data.  Draw a fresh 32-byte seed from the
+  // caller's RNG for every call (what the Rust shim does, rust/halo2_proofs_patch/src/gpu.rs) or advance proof_index.
   // Proof::create (proof.rs:25-42).  `instance`: one vector per instance column (&[&[pallas::Base]]); `rng_seed`: 32 bytes
   // the caller draws from its RNG (the reference passes `impl RngCore`), from which every blinding scalar is derived.
   // Throws Error (kind() == "ConstraintSystemFailure" for a lookup input outside its table).

@@ -30,6 +30,7 @@ struct Circuit {
   // device tables
   Fp *fixed_vals = nullptr, *fixed_polys = nullptr, *fixed_cosets = nullptr, *sig_vals = nullptr, *sig_polys = nullptr, *sig_cosets = nullptr;
   Fp *l0 = nullptr, *l_last = nullptr, *l_blind = nullptr, *consts = nullptr, *wr_inv = nullptr;
+  Fp* coset_pre = nullptr;   // [R][n]: zeta^(i mod 3) * w_ext^(i * k1), the factor the forward coset NTT applies to coefficient i for sub-coset k1
   int2 *d_aq = nullptr, *d_fq = nullptr, *d_iq = nullptr, *d_perm = nullptr;
   QProgram prog_lookups;
   // gate programs keyed by number of parts: `gate_parts` holds the constraints evaluated on every sub-coset (all of them when the
@@ -58,7 +59,7 @@ struct Circuit {
   ~Circuit() {
     for (auto& kv : ws) { for (auto& b : kv.second->blocks) cudaFree(b.p); for (void* p : kv.second->tables) cudaFree(p); }
     for (void* p : {(void*)fixed_vals, (void*)fixed_polys, (void*)fixed_cosets, (void*)sig_vals, (void*)sig_polys, (void*)sig_cosets, (void*)l0, (void*)l_last,
-                    (void*)l_blind, (void*)consts, (void*)wr_inv, (void*)d_aq, (void*)d_fq, (void*)d_iq, (void*)d_perm, (void*)prog_lookups.dev})
+                    (void*)l_blind, (void*)consts, (void*)wr_inv, (void*)coset_pre, (void*)d_aq, (void*)d_fq, (void*)d_iq, (void*)d_perm, (void*)prog_lookups.dev})
       if (p) cudaFree(p);
     for (auto& kv : gate_parts) for (auto& qp : kv.second) if (qp.dev) cudaFree(qp.dev);
     for (auto& kv : gate_parts_lo) for (auto& qp : kv.second) if (qp.dev) cudaFree(qp.dev);

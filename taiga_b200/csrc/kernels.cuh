@@ -9,7 +9,10 @@ namespace tb {
 //   v *= zeta^(idx mod 3)            (halo2 `distribute_powers_zeta`)           if use_zeta (z1 = zeta^1, z2 = zeta^2 or inverses)
 //   v *= w_{2^mod_bits}^(idx * k)    (sub-coset shift, same direction as the transform's twiddles)   if k != 0
 //   v *= c                                                                           if use_const
-template <class F> struct NttHook { int use_zeta; F z1, z2; uint32_t k; int mod_bits; int use_const; F c; };
+//   v *= table[idx]                  (all of the above precomputed per element: one multiplication, one coalesced load)   if table
+template <class F> struct NttHook { int use_zeta; F z1, z2; uint32_t k; int mod_bits; int use_const; F c; const F* table = nullptr; };
+// table[i] = what `hook` multiplies element i by, i < n (built once per circuit for the forward coset hooks)
+template <class F> void ntt_hook_table(Ctx* ctx, const NttHook<F>& hook, bool inverse, F* table, int n);
 
 template <class F>
 void ntt_run(Ctx* ctx, int logn, bool inverse, const F* in, F* out, F* scratch, int batch, long long in_bstride,

@@ -33,6 +33,7 @@ struct NttArgs {
 
 template <class F>
 __device__ __forceinline__ F apply_hook(const NttHook<F>& h, const TwiddleTables<F>& tw, F v, uint32_t idx) {
+  if (h.table) return v * ldg_fe(h.table + idx);
   if (h.use_zeta) { uint32_t m3 = idx % 3u; if (m3) v = v * (m3 == 1 ? h.z1 : h.z2); }
   if (h.k) {
     uint32_t e = (uint32_t)(((uint64_t)idx * h.k) & ((1ull << h.mod_bits) - 1)) << (TW_LOG - h.mod_bits);
@@ -131,14 +132,10 @@ void ntt_run(Ctx* ctx, int logn, bool inverse, const F* in, F* out, F* scratch, 
   TB_REQUIRE(batch >= 1 && batch <= 65535 && batch2 >= 1 && batch2 <= 65535, "NTT batch out of range");
   ProfScope prof_scope(ctx, PC_NTT);
   { const double elems = (double)batch * batch2 * (double)(1ull << logn);
-    const double hook = (pre ? (pre->use_zeta ? 0.67 : 0.0) + (pre->k ? 1.0 : 0.0) + (pre->use_const ? 1.0 : 0.0) : 0.0) +
+    const double hook = (pre ? (pre->table ? 1.0 : (pre->use_zeta ? 0.67 : 0.0) + (pre->k ? 1.0 : 0.0) + (pre->use_const ? 1.0 : 0.0)) : 0.0) +
                         ((post || inverse) ? 1.0 + (post && post->k ? 1.0 : 0.0) + (post && post->use_zeta ? 0.67 : 0.0) : 0.0);
     ctx->work[PC_NTT] += elems * (0.5 * logn + hook + (logn > 10 ? 1.0 : 0.0)); }   // butterflies + hooks + inter-pass twiddles
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[F::params_id()]) {
-    TB_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set[F::params_id()] = true;
-  }
+  ctx->opt_in_smem(ntt_pass_kernel<F>, 96 * 1024);
   NttArgs<F> a;
   a.tw = inverse ? field_tables<F>(ctx).inv : field_tables<F>(ctx).fwd;
   a.logn = logn;
@@ -175,6 +172,19 @@ void ntt_run(Ctx* ctx, int logn, bool inverse, const F* in, F* out, F* scratch, 
 
 template void ntt_run<Fp>(Ctx*, int, bool, const Fp*, Fp*, Fp*, int, long long, long long, const NttHook<Fp>*, const NttHook<Fp>*, int, long long, long long);
 template void ntt_run<Fq>(Ctx*, int, bool, const Fq*, Fq*, Fq*, int, long long, long long, const NttHook<Fq>*, const NttHook<Fq>*, int, long long, long long);
+
+template <class F>
+__global__ void ntt_hook_table_kernel(NttHook<F> h, TwiddleTables<F> tw, F* table, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) st_fe(table + i, apply_hook(h, tw, F::one(), (uint32_t)i));
+}
+template <class F> void ntt_hook_table(Ctx* ctx, const NttHook<F>& hook, bool inverse, F* table, int n) {
+  NttHook<F> h = hook; h.table = nullptr;
+  ntt_hook_table_kernel<F><<<(n + 255) / 256, 256, 0, ctx->stream>>>(h, inverse ? field_tables<F>(ctx).inv : field_tables<F>(ctx).fwd, table, n);
+  TB_LAUNCH_CHECK();
+}
+template void ntt_hook_table<Fp>(Ctx*, const NttHook<Fp>&, bool, Fp*, int);
+template void ntt_hook_table<Fq>(Ctx*, const NttHook<Fq>&, bool, Fq*, int);
 
 // ---- twiddle table construction (host arithmetic with the same field code, uploaded once per context)
 template <class F>

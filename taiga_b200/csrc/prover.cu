@@ -27,7 +27,8 @@ static Fp* dev_alloc_fp(size_t count) { Fp* p = nullptr; TB_CUDA(cudaMalloc(&p, 
 
 static NttHook<Fp> coset_hook(const Circuit& C, int k1, bool inverse) {
   NttHook<Fp> h; h.use_const = 0; h.mod_bits = C.ext_k; h.k = (uint32_t)k1;
-  if (!inverse) { h.use_zeta = 1; h.z1 = C.zeta; h.z2 = C.zeta.sqr(); } else { h.use_zeta = 0; h.z1 = Fp::one(); h.z2 = Fp::one(); }
+  if (!inverse) { h.use_zeta = 1; h.z1 = C.zeta; h.z2 = C.zeta.sqr(); if (C.coset_pre) h.table = C.coset_pre + (size_t)k1 * C.n; }
+  else { h.use_zeta = 0; h.z1 = Fp::one(); h.z2 = Fp::one(); }
   return h;
 }
 // polys [count][n] -> cosets [count][R][n] (sub-coset major)
@@ -114,6 +115,12 @@ static Circuit* circuit_load(Ctx* ctx, const Srs* srs, const tb_cs_desc* cs, con
   C.d_aq = dev_upload(q2(C.aq)); C.d_fq = dev_upload(q2(C.fq)); C.d_iq = dev_upload(q2(C.iq));
   { std::vector<int2> pc; for (auto& c : C.perm) pc.push_back(make_int2((int)c.kind, (int)c.index)); C.d_perm = dev_upload(pc); }
 
+  { // per-element factors of the forward coset hooks (one multiplication per coefficient instead of up to two and a table walk)
+    Fp* tab = dev_alloc_fp((size_t)C.R * n);
+    for (int k1 = 0; k1 < C.R; ++k1) { NttHook<Fp> h = coset_hook(C, k1, false); ntt_hook_table<Fp>(ctx, h, false, tab + (size_t)k1 * n, (int)n); }
+    ctx->sync();
+    if (tb_tune("TB_NTT_HOOK_TABLE", 1)) C.coset_pre = tab; else cudaFree(tab);
+  }
   DevBuf<Fp> scratch(ctx, std::max<size_t>(3, std::max<size_t>(C.nf, C.P)) * n);
   auto load_cols = [&](const uint8_t* src, size_t cnt, Fp*& vals, Fp*& polys, Fp*& cosets) {
     vals = dev_alloc_fp(cnt * n); polys = dev_alloc_fp(cnt * n); cosets = dev_alloc_fp(cnt * C.R * n);

@@ -109,3 +109,18 @@ def test_tuning_knobs_do_not_change_results(gpu_ctx, oracle_cpu, monkeypatch):
         assert pk.prove_batch(adv, inst, lens, seed) == ref, knobs
         for k_ in knobs:
             monkeypatch.delenv(k_)
+
+
+def test_cpp_host_mirror_proves_and_verifies_on_the_gpu(tmp_path):
+    """include/taiga_b200.hpp + examples/prove_cpp.cpp (the C++ mirror of Proof::create / Proof::verify, proof.rs:25-54) on real
+    hardware: builds with the host compiler, creates a proof through the C ABI, verifies it and rejects a wrong instance."""
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "prove_cpp")
+    libdir = os.path.dirname(lib.LIB_PATH)
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "prove_cpp.cpp"),
+                        "-L", libdir, "-ltaiga_b200", "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "created and verified" in r.stdout and "wrong instance rejected" in r.stdout

@@ -14,7 +14,8 @@ s = rng.integers(0, 256, size=(K, N15, 32), dtype=np.uint8); s[:, :, 31] &= 0x3F
 bl = np.zeros((K, 32), np.uint8)
 os.environ["TB_MSM_BA_MIN_TERMS"] = "0"
 ref = None
-for cfg in [{}, {"TB_MSM_BA_M": "8"}, {"TB_MSM_BA_M": "32"}, {"TB_MSM_BA_MINB": "2"}, {"TB_MSM_BA_MINB": "4"}, {"TB_MSM_BA_M": "32", "TB_MSM_BA_MINB": "4"}, {"TB_MSM_BA_M": "8", "TB_MSM_BA_MINB": "4"},
+CONFIGS = None
+for cfg in CONFIGS or [{}, {"TB_MSM_BA_M": "8"}, {"TB_MSM_BA_M": "32"}, {"TB_MSM_BA_MINB": "2"}, {"TB_MSM_BA_MINB": "4"}, {"TB_MSM_BA_M": "32", "TB_MSM_BA_MINB": "4"}, {"TB_MSM_BA_M": "8", "TB_MSM_BA_MINB": "4"},
             {"TB_MSM_BA_ROUNDS": "8"}, {"TB_MSM_BA_ROUNDS": "9"}, {"TB_MSM_BA_CHUNK": "704"}, {}]:
     os.environ.update(cfg)
     out = srs.commit(s, bl, lagrange=True, batch=K)
