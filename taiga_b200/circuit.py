@@ -219,10 +219,14 @@ class Assignment:
 
 
 def _col_bytes(dicts, n):
+    """{row: value} per column -> [columns, n, 32] little-endian bytes (one join + one scatter per column)."""
     out = np.zeros((len(dicts), n, 32), np.uint8)
     for c, d in enumerate(dicts):
-        for row, v in d.items():
-            out[c, row] = np.frombuffer(int(v).to_bytes(32, "little"), np.uint8)
+        if not d:
+            continue
+        rows = np.fromiter(d.keys(), dtype=np.int64, count=len(d))
+        vals = np.frombuffer(b"".join([int(v).to_bytes(32, "little") for v in d.values()]), np.uint8).reshape(len(d), 32)
+        out[c, rows] = vals
     return out
 
 

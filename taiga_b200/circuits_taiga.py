@@ -419,9 +419,18 @@ class Shape:
         """Fixed-base scalar mul: per window a 3-bit digit w, the lagrange coefficient columns interpolate x(w); y by curve equation."""
         adv, lg = self.adv, self.lagrange
         for _ in range(windows):
-            # fixed: 8 window points and the coefficients interpolating x(w), w = 0..7 (what halo2's fixed-base tables hold)
-            pts = [_rand_point(self.frnd) for _ in range(8)]
-            coeffs = _interpolate8([p_[0] for p_ in pts])
+            # fixed: 8 window points and the coefficients interpolating x(w), w = 0..7 (what halo2's fixed-base tables hold).
+            # They depend on the fixed RNG stream only, so the first synthesis records them (with the RNG state that follows) and
+            # every later witness replays them: 2040 modular square roots per Compliance witness were 70 % of its synthesis time.
+            ci = self._fixed_cursor
+            self._fixed_cursor += 1
+            if ci < len(self._fixed_cache):
+                pts, coeffs, state = self._fixed_cache[ci]
+                self.frnd.setstate(state)
+            else:
+                pts = [_rand_point(self.frnd) for _ in range(8)]
+                coeffs = _interpolate8([p_[0] for p_ in pts])
+                self._fixed_cache.append((pts, coeffs, self.frnd.getstate()))
             for i in range(8):
                 asg.assign(lg[i], row, coeffs[i])
             w = rnd.randrange(8)
@@ -491,6 +500,9 @@ class Shape:
     def synthesize(self, k, wseed):
         rnd = random.Random(wseed)           # witness values
         self.frnd = random.Random(0xF1ED)    # fixed-column values and region structure: identical for every witness
+        self._fixed_cursor = 0
+        if not hasattr(self, "_fixed_cache"):
+            self._fixed_cache = []
         asg = Assignment(self.cs, k)
         adv = self.adv
         for i in range(1 << K_LOOKUP):

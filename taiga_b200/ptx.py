@@ -60,14 +60,17 @@ class ProverService:
         self.contexts = [w[0] for w in self.c_workers + self.v_workers]
 
     def synthesize_ptx(self, n_ptx, wseed=0, procs=None):
-        """Witness tables for n_ptx partial transactions: dict of stacked numpy arrays (host)."""
-        jobs = [(True, wseed * 100000 + i) for i in range(COMPLIANCE_PER_PTX * n_ptx)] + \
-               [(False, wseed * 100000 + 50000 + i) for i in range(VP_PER_PTX * n_ptx)]
-        res = _synthesize_many(self, jobs, procs)
-        cw, vw = res[:COMPLIANCE_PER_PTX * n_ptx], res[COMPLIANCE_PER_PTX * n_ptx:]
+        """Witness tables for n_ptx partial transactions: dict of stacked numpy arrays (host).  The advice tables (60 MiB per ptx)
+        are written by the worker processes straight into shared memory; only the small instance vectors travel through pipes."""
+        nc, nv = COMPLIANCE_PER_PTX * n_ptx, VP_PER_PTX * n_ptx
+        jobs = [(True, wseed * 100000 + i, i) for i in range(nc)] + [(False, wseed * 100000 + 50000 + i, i) for i in range(nv)]
+        c_adv = _shared_array((nc, self.kd_c.cs.num_advice, self.kd_c.n, 32))
+        v_adv = _shared_array((nv, self.kd_v.cs.num_advice, self.kd_v.n, 32))
+        res = _synthesize_many(self, jobs, procs, c_adv, v_adv)
+        cw, vw = res[:nc], res[nc:]
         return {
-            "c_adv": np.stack([w[0] for w in cw]), "c_inst": np.stack([w[1] for w in cw]), "c_len": cw[0][2],
-            "v_adv": np.stack([w[0] for w in vw]), "v_inst": np.stack([w[1] for w in vw]), "v_len": vw[0][2],
+            "c_adv": c_adv, "c_inst": np.stack([w[0] for w in cw]), "c_len": cw[0][1],
+            "v_adv": v_adv, "v_inst": np.stack([w[0] for w in vw]), "v_len": vw[0][1],
         }
 
     def build_ptx_batch(self, wit, seed, c_adv=None, v_adv=None, max_batch=64, workers_per_circuit=None):
@@ -149,30 +152,50 @@ class ProverService:
         return out
 
 
-_SYNTH_SVC = None
+_SYNTH = None
+
+
+def _shared_array(shape):
+    """uint8 array in anonymous shared memory (inherited by forked workers; unlinked at once, freed with the last mapping)."""
+    from multiprocessing import shared_memory
+    size = int(np.prod(shape))
+    shm = shared_memory.SharedMemory(create=True, size=max(1, size))
+    arr = np.ndarray(shape, dtype=np.uint8, buffer=shm.buf)
+    try:
+        shm.unlink()
+    except Exception:
+        pass
+    _KEEP.append(shm)   # the mapping must outlive the array
+    return arr
+
+
+_KEEP = []
 
 
 def _synth_one(job):
-    comp, seed = job
-    svc = _SYNTH_SVC
-    return (svc.kd_c.witness_arrays(svc.make_c(seed)) if comp else svc.kd_v.witness_arrays(svc.make_v(seed)))
+    comp, seed, slot = job
+    svc, c_adv, v_adv = _SYNTH
+    kd, make, out = (svc.kd_c, svc.make_c, c_adv) if comp else (svc.kd_v, svc.make_v, v_adv)
+    adv, inst, lens = kd.witness_arrays(make(seed))
+    out[slot] = adv
+    return inst, lens
 
 
-def _synthesize_many(svc, jobs, procs=None):
+def _synthesize_many(svc, jobs, procs, c_adv, v_adv):
     """Host witness synthesis (the stand-in for the Rust `Circuit::synthesize`, compliance_circuit.rs:174-327) of many
     proofs: forked worker processes, one witness per task."""
-    global _SYNTH_SVC
+    global _SYNTH
     import multiprocessing as mp
     import os
     procs = procs or min(len(jobs), max(1, (os.cpu_count() or 2) - 2), 64)
-    _SYNTH_SVC = svc
+    _SYNTH = (svc, c_adv, v_adv)
     try:
-        if procs <= 1 or len(jobs) <= 2:
+        if procs <= 1 or len(jobs) <= 6:
             return [_synth_one(j) for j in jobs]
         with mp.get_context("fork").Pool(procs) as pool:
-            return pool.map(_synth_one, jobs, chunksize=1)
+            return pool.map(_synth_one, jobs, chunksize=max(1, len(jobs) // (4 * procs)))
     finally:
-        _SYNTH_SVC = None
+        _SYNTH = None
 
 
 class _TensorSlice:
