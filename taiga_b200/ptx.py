@@ -14,6 +14,7 @@ The circuits are the Taiga-shaped ones of circuits_taiga.py (the real ones need 
 synthesis happens on the host before the call, exactly as `Circuit::synthesize` does in the reference; it is not part
 of the proving hot path and not part of any timed region.
 """
+import os
 import threading
 
 import numpy as np
@@ -59,9 +60,12 @@ class ProverService:
         self.pk_c, self.pk_v = self.c_workers[0][1], self.v_workers[0][1]
         self.contexts = [w[0] for w in self.c_workers + self.v_workers]
 
-    def synthesize_ptx(self, n_ptx, wseed=0, procs=None):
+    def synthesize_ptx(self, n_ptx, wseed=0, procs=None, pool=None):
         """Witness tables for n_ptx partial transactions: dict of stacked numpy arrays (host).  The advice tables (60 MiB per ptx)
-        are written by the worker processes straight into shared memory; only the small instance vectors travel through pipes."""
+        are written by the worker processes straight into shared memory; only the small instance vectors travel through pipes.
+        `pool`: a SynthPool started before any CUDA work (no fork from a multi-threaded process); default: fork here."""
+        if pool is not None:
+            return pool.synthesize(n_ptx, wseed)
         nc, nv = COMPLIANCE_PER_PTX * n_ptx, VP_PER_PTX * n_ptx
         jobs = [(True, wseed * 100000 + i, i) for i in range(nc)] + [(False, wseed * 100000 + 50000 + i, i) for i in range(nv)]
         c_adv = _shared_array((nc, self.kd_c.cs.num_advice, self.kd_c.n, 32))
@@ -196,6 +200,73 @@ def _synthesize_many(svc, jobs, procs, c_adv, v_adv):
             return pool.map(_synth_one, jobs, chunksize=max(1, len(jobs) // (4 * procs)))
     finally:
         _SYNTH = None
+
+
+# ---- persistent pool of synthesis workers (started before CUDA is initialised; the workers build the circuits themselves)
+_W = {}
+
+
+def _pool_init():
+    _W["c"] = circuits_taiga.build(True)
+    _W["v"] = circuits_taiga.build(False)
+
+
+def _pool_job(job):
+    comp, seed, slot, name, shape = job
+    import mmap
+    kd, make = _W["c" if comp else "v"]
+    adv, inst, lens = kd.witness_arrays(make(seed))
+    key = "map_c" if comp else "map_v"
+    m = _W.get(key)
+    if m is None or m[0] != name:   # map the batch's segment once per worker (plain mmap: no resource-tracker traffic)
+        if m is not None:
+            del _W[key]
+            m = None
+        fd = os.open("/dev/shm/" + name.lstrip("/"), os.O_RDWR)
+        try:
+            mm = mmap.mmap(fd, int(np.prod(shape)))
+        finally:
+            os.close(fd)
+        m = _W[key] = (name, np.frombuffer(mm, dtype=np.uint8).reshape(shape), mm)
+    m[1][slot] = adv
+    return inst, lens
+
+
+class SynthPool:
+    """Worker processes for host witness synthesis (stand-in for the Rust `Circuit::synthesize`).  Create it BEFORE torch / CUDA
+    are touched: the workers are forked once from a single-threaded parent and live for the whole run."""
+
+    def __init__(self, procs=None):
+        import multiprocessing as mp
+        import os
+        self.procs = procs or min(64, max(1, (os.cpu_count() or 2) - 2))
+        self.pool = mp.get_context("fork").Pool(self.procs, initializer=_pool_init)
+
+    def synthesize(self, n_ptx, wseed=0):
+        from multiprocessing import shared_memory
+        nc, nv = COMPLIANCE_PER_PTX * n_ptx, VP_PER_PTX * n_ptx
+        n15 = 1 << 15
+        shapes = {True: (nc, 10, n15, 32), False: (nv, 10, n15, 32)}
+        shms = {c: shared_memory.SharedMemory(create=True, size=int(np.prod(sh))) for c, sh in shapes.items()}
+        try:
+            jobs = [(True, wseed * 100000 + i, i, shms[True].name, shapes[True]) for i in range(nc)] + \
+                   [(False, wseed * 100000 + 50000 + i, i, shms[False].name, shapes[False]) for i in range(nv)]
+            res = self.pool.map(_pool_job, jobs, chunksize=max(1, len(jobs) // (4 * self.procs)))
+        finally:
+            for sh in shms.values():
+                try:
+                    sh.unlink()
+                except Exception:
+                    pass
+        _KEEP.extend(shms.values())
+        c_adv = np.ndarray(shapes[True], dtype=np.uint8, buffer=shms[True].buf)
+        v_adv = np.ndarray(shapes[False], dtype=np.uint8, buffer=shms[False].buf)
+        cw, vw = res[:nc], res[nc:]
+        return {"c_adv": c_adv, "c_inst": np.stack([w[0] for w in cw]), "c_len": cw[0][1],
+                "v_adv": v_adv, "v_inst": np.stack([w[0] for w in vw]), "v_len": vw[0][1]}
+
+    def close(self):
+        self.pool.terminate()
 
 
 class _TensorSlice:
