@@ -310,7 +310,8 @@ def main():
         return
 
     from taiga_b200 import ptx, shard
-    spool = ptx.SynthPool(int(os.environ.get("TB_SYNTH_PROCS", 0)) or None)   # forked before CUDA / threads exist
+    # witness-synthesis workers, forked before CUDA / threads exist; the host cores are shared by the ranks of a multi-GPU run
+    spool = ptx.SynthPool(int(os.environ.get("TB_SYNTH_PROCS", 0)) or min(64, max(4, ((os.cpu_count() or 8) - 2) // max(1, world))))
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
