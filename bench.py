@@ -376,7 +376,7 @@ def main():
     # configs[1]: one partial transaction per step, two streams per circuit (latency-bound; secondary figure)
     latency = None
     if not args.no_latency and P > 1:
-        w1 = {k_: (v_[:2] if k_.startswith("c_") and k_ != "c_len" else v_[:4] if k_.startswith("v_") and k_ != "v_len" else v_) for k_, v_ in wit.items()}
+        w1 = {k_: (v_[:2] if k_.startswith("c_") and k_ != "c_len" else v_[:4] if k_.startswith("v_") and k_ != "v_len" else v_) for k_, v_ in wit.items() if not k_.startswith("_")}
         c1, v1 = c_dev[:2], v_dev[:4]
         lsteps = max(5, args.steps)
         _, lw, ll, _ = timed(True, lsteps, 3, w=w1, cd=c1, vd=v1, nw=nw_lat)
@@ -391,8 +391,13 @@ def main():
     if not args.no_synth_pipeline and P > 1:
         nxt = {}
 
+        rt = torch.cuda.cudart()
+
         def synth(i):
-            nxt[i] = svc.synthesize_ptx(P, wseed=1000 + 10 * rank + i, pool=spool)
+            w_ = svc.synthesize_ptx(P, wseed=1000 + 10 * rank + i, pool=spool)
+            for key in ("c_adv", "v_adv"):   # page-lock the shared memory in the background so that the upload is one fast DMA
+                rt.cudaHostRegister(w_[key].ctypes.data, w_[key].nbytes, 0)
+            nxt[i] = w_
         th = threading.Thread(target=synth, args=(0,))
         th.start()
         th.join()
@@ -406,14 +411,19 @@ def main():
             th = threading.Thread(target=synth, args=(i + 1,))
             th.start()
             step(200 + i, False, w=cur, cd=cur["c_adv"], vd=cur["v_adv"])
+            for key in ("c_adv", "v_adv"):
+                rt.cudaHostUnregister(cur[key].ctypes.data)
             th.join()
         torch.cuda.synchronize()
         pw = torch.tensor([(time.time() - t0) * 1e3], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(pw, op=dist.ReduceOp.MAX)
+        for w_ in nxt.values():
+            for key in ("c_adv", "v_adv"):
+                rt.cudaHostUnregister(w_[key].ctypes.data)
         nxt.clear()
         synth_pipe = {"value": round(P * world / (float(pw[0]) * 1e-3 / psteps), 4), "unit": "ptx/s", "steps": psteps,
-                      "note": "fresh witnesses every step, synthesised by forked host processes while the previous step is proved; advice read from pageable shared memory"}
+                      "note": "fresh witnesses every step, synthesised by forked host processes while the previous step is proved; advice page-locked in the background (cudaHostRegister) and uploaded through the C ABI"}
 
     # one profiled step (CUDA events around every kernel group) for the share-of-step table and the roofline.  It runs the
     # workers one after the other: with the streams overlapped an event pair also times the wait for SMs held by the other

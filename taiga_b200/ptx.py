@@ -258,12 +258,12 @@ class SynthPool:
                     sh.unlink()
                 except Exception:
                     pass
-        _KEEP.extend(shms.values())
         c_adv = np.ndarray(shapes[True], dtype=np.uint8, buffer=shms[True].buf)
         v_adv = np.ndarray(shapes[False], dtype=np.uint8, buffer=shms[False].buf)
         cw, vw = res[:nc], res[nc:]
         return {"c_adv": c_adv, "c_inst": np.stack([w[0] for w in cw]), "c_len": cw[0][1],
-                "v_adv": v_adv, "v_inst": np.stack([w[0] for w in vw]), "v_len": vw[0][1]}
+                "v_adv": v_adv, "v_inst": np.stack([w[0] for w in vw]), "v_len": vw[0][1],
+                "_shm": list(shms.values())}   # the (already unlinked) segments live exactly as long as this dictionary
 
     def close(self):
         self.pool.terminate()
