@@ -518,7 +518,7 @@ def main():
                    "hbm_resident_gb": round(torch.cuda.memory_allocated() / 1e9, 1), "proofs_accepted_by_oracle_verifier": accepted, "proofs_accepted_by_device_verifier": accepted_dev},
         "e2e": {"value": round(e2e_val, 4), "unit": "ptx/s", "ms_per_step": round(e2e_step_ms, 3), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "device_event_ms_per_step": round(dev_ms / args.steps, 3),
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "gpu_launches_per_proof": round(launches / max(1, args.steps * 6 * P), 1), "clocks": clocks,
         "roofline": roof,
         "profile_share": {k: round(v[0] / tot_prof, 4) for k, v in sorted(prof.items(), key=lambda kv_: -kv_[1][0])},
         "profile_ms": {k: round(v[0], 3) for k, v in prof.items()},
