@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <algorithm>
 #include <memory>
+#include <type_traits>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -110,7 +111,10 @@ __global__ void __launch_bounds__(SORT_THREADS) msm_sort_kernel(const __grid_con
   __syncthreads();
   uint32_t* ent = entries + (long long)k * cap0;
 
-  auto digits = [&](const S& sm, uint32_t idx, bool scatter) {
+  // `scatter` is a compile-time constant of each pass: the histogram pass issues its shared-memory atomics without waiting for a
+  // return value (no scoreboard stall), only the scatter pass needs the old counter
+  auto digits = [&](const S& sm, uint32_t idx, auto scatter_c) {
+    constexpr bool scatter = decltype(scatter_c)::value;
     S s = sm.from_mont();
     if (s.is_zero()) return;
     uint32_t carry = 0;
@@ -122,8 +126,8 @@ __global__ void __launch_bounds__(SORT_THREADS) msm_sort_kernel(const __grid_con
       uint32_t v = ((uint32_t)(v64 >> off) & ((1u << c) - 1)) + carry, neg = 0;
       if (v > half) { v = (1u << c) - v; neg = 1; carry = 1; } else carry = 0;
       if (v) {
-        uint32_t pos = atomicAdd(&hist[v - 1], 1u);
-        if (scatter) ent[pos] = (uint32_t)(w * table_stride + idx) | (neg << 31);
+        if (scatter) { const uint32_t pos = atomicAdd(&hist[v - 1], 1u); ent[pos] = (uint32_t)(w * table_stride + idx) | (neg << 31); }
+        else atomicAdd(&hist[v - 1], 1u);
       }
     }
   };
@@ -142,10 +146,10 @@ __global__ void __launch_bounds__(SORT_THREADS) msm_sort_kernel(const __grid_con
       if (t == 0 && it + 1 < ntiles) issue(st ^ 1, it + 1);   // the other stage: its readers finished before the last barrier
       mbar_wait(&bars[st], phase[st]); phase[st] ^= 1;
       const int i = it * SORT_TILE + t;
-      if (i < N) digits(tile[st * SORT_TILE + t], (uint32_t)i, pass == 1);
+      if (i < N) { if (pass) digits(tile[st * SORT_TILE + t], (uint32_t)i, std::true_type()); else digits(tile[st * SORT_TILE + t], (uint32_t)i, std::false_type()); }
       __syncthreads();   // everybody is done with stage st before it is refilled
     }
-    if (t < n_extra) digits(ldg_fe(extras + (long long)k * n_extra + t), (uint32_t)(N + t), pass == 1);
+    if (t < n_extra) { const S ex = ldg_fe(extras + (long long)k * n_extra + t); if (pass) digits(ex, (uint32_t)(N + t), std::true_type()); else digits(ex, (uint32_t)(N + t), std::false_type()); }
     __syncthreads();
     if (pass == 0) {
       for (int b = t; b < NB; b += SORT_THREADS) counts[(long long)k * NB + b] = hist[b];
@@ -182,10 +186,17 @@ struct RoundOffsets {
     block_scan_excl(off_nxt, NB, tmp);
     n_next = off_nxt[NB];
   }
-  // output item q -> position of its first input, and whether a second input exists
-  __device__ __forceinline__ void locate(uint32_t q, int NB, uint32_t& in0, bool& two) const {
-    int lo = 0, hi = NB;   // largest b with off_nxt[b] <= q
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off_nxt[mid] <= q) lo = mid; else hi = mid; }
+  // output item q -> position of its first input, and whether a second input exists.  `hint`: a bucket at or before the one of q
+  // (the previous item of the same thread): a few steps forward usually find it, a binary search takes over otherwise.
+  __device__ __forceinline__ void locate(uint32_t q, int NB, uint32_t& in0, bool& two, int& hint) const {
+    int lo = hint;   // invariant: off_nxt[lo] <= q
+#pragma unroll 1
+    for (int s = 0; s < 6 && off_nxt[lo + 1] <= q; ++s) ++lo;
+    if (off_nxt[lo + 1] <= q) {
+      int hi = NB;   // largest b with off_nxt[b] <= q
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off_nxt[mid] <= q) lo = mid; else hi = mid; }
+    }
+    hint = lo;
     in0 = off_cur[lo] + 2 * (q - off_nxt[lo]);
     two = in0 + 1 < off_cur[lo + 1];
   }
@@ -249,11 +260,12 @@ __global__ void __launch_bounds__(BA_THREADS) msm_ba_fwd_kernel(const uint32_t* 
   B* pre_k = pre + (long long)k * cap_out;
   uint32_t* meta_k = meta + (long long)k * cap_out;
   B acc = B::one();
+  int hint = 0;
 #pragma unroll 1
   for (int i = 0; i < M; ++i) {
     const uint32_t q = Q0 + (uint32_t)i * BA_THREADS + t;
     if (q >= ro.n_next) break;
-    uint32_t in0; bool two; ro.locate(q, NB, in0, two);
+    uint32_t in0; bool two; ro.locate(q, NB, in0, two, hint);
     meta_k[q] = in0 | (two ? 0x80000000u : 0u);   // the backward kernel does not search again
     st_fe(pre_k + q, acc);
     if (!two) continue;
