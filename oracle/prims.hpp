@@ -6,7 +6,10 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <atomic>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <thread>
 #include "field.hpp"
 
@@ -14,14 +17,79 @@ namespace orc {
 
 inline int& num_threads() { static int n = std::max(1u, std::thread::hardware_concurrency()); return n; }
 
-// halo2 `parallelize`: split [0,n) into contiguous chunks, one per thread
-inline void parallel_for(size_t n, const std::function<void(size_t, size_t)>& f) {
-  int nt = num_threads();
-  if (nt <= 1 || n < 64) { f(0, n); return; }
-  size_t chunk = (n + nt - 1) / nt;
-  std::vector<std::thread> th;
-  for (size_t s = 0; s < n; s += chunk) th.emplace_back(f, s, std::min(n, s + chunk));
-  for (auto& t : th) t.join();
+// A persistent pool of worker threads, the counterpart of the rayon pool behind halo2's `multicore` feature: the prover calls
+// `parallelize` thousands of times per proof (every FFT stage), so spawning threads per call -- what this file used to do --
+// cost more than the arithmetic on a 128-thread host and made the CPU baseline look slower than the algorithm is.
+class Pool {
+ public:
+  static Pool& get() { static Pool p; return p; }
+  // runs task(0) .. task(count - 1) on up to `count` threads (the caller takes part); returns when all are done
+  void run(size_t count, const std::function<void(size_t)>& task) {
+    if (count == 0) return;
+    if (count == 1 || in_task() || workers_.empty()) { for (size_t i = 0; i < count; ++i) task(i); return; }
+    std::unique_lock<std::mutex> job_lock(job_mu_);   // one job at a time
+    { std::lock_guard<std::mutex> lk(mu_);
+      task_ = &task; count_ = count; next_.store(0); pending_.store(count); ++epoch_; }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return pending_.load() == 0 && active_ == 0; });   // nobody is still polling this job's counter
+    task_ = nullptr;
+  }
+  ~Pool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; ++epoch_; }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+
+ private:
+  Pool() {
+    unsigned n = std::max(1u, std::thread::hardware_concurrency());
+    for (unsigned i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  static bool& in_task() { static thread_local bool f = false; return f; }
+  void work() {
+    in_task() = true;
+    for (;;) {
+      size_t i = next_.fetch_add(1);
+      if (i >= count_) break;
+      (*task_)(i);
+      if (pending_.fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(mu_); done_cv_.notify_all(); }
+    }
+    in_task() = false;
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      { std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (stop_) return;
+        if (!task_) continue;
+        ++active_; }
+      work();
+      { std::lock_guard<std::mutex> lk(mu_); --active_; }
+      done_cv_.notify_all();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_, job_mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(size_t)>* task_ = nullptr;
+  size_t count_ = 0;
+  std::atomic<size_t> next_{0}, pending_{0};
+  uint64_t epoch_ = 0;
+  int active_ = 0;   // workers inside work() (guarded by mu_)
+  bool stop_ = false;
+};
+
+// halo2 `parallelize`: split [0,n) into contiguous chunks, one per thread (at least `grain` elements each)
+inline void parallel_for(size_t n, const std::function<void(size_t, size_t)>& f, size_t grain = 128) {
+  size_t nt = (size_t)num_threads();
+  if (nt > n / grain) nt = n / grain;
+  if (nt <= 1) { f(0, n); return; }
+  const size_t chunk = (n + nt - 1) / nt, parts = (n + chunk - 1) / chunk;
+  Pool::get().run(parts, [&](size_t t) { f(t * chunk, std::min(n, (t + 1) * chunk)); });
 }
 
 // ---- best_multiexp (bucket method, window c = ceil(ln n), no precomputation, per-thread chunks)
@@ -55,10 +123,7 @@ Jac<F> best_multiexp(const u64 (*scalars)[4], const Affine<F>* bases, size_t n) 
   if (nt <= 1 || n < (size_t)nt * 16) return multiexp_serial<F>(scalars, bases, n);
   size_t chunk = (n + nt - 1) / nt;
   std::vector<Jac<F>> parts((n + chunk - 1) / chunk);
-  std::vector<std::thread> th;
-  for (size_t t = 0; t < parts.size(); ++t)
-    th.emplace_back([&, t]() { size_t s = t * chunk, e = std::min(n, s + chunk); parts[t] = multiexp_serial<F>(scalars + s, bases + s, e - s); });
-  for (auto& t : th) t.join();
+  Pool::get().run(parts.size(), [&](size_t t) { size_t s = t * chunk, e = std::min(n, s + chunk); parts[t] = multiexp_serial<F>(scalars + s, bases + s, e - s); });
   Jac<F> acc = Jac<F>::identity();
   for (auto& p : parts) acc = acc.add(p);
   return acc;
@@ -145,14 +210,11 @@ template <class Sc> Sc eval_polynomial(const Sc* c, size_t n, const Sc& x) {
   if (nt <= 1 || n < 1024) { Sc acc = Sc::zero(); for (size_t i = n; i-- > 0;) acc = acc * x + c[i]; return acc; }
   size_t chunk = (n + nt - 1) / nt, parts = (n + chunk - 1) / chunk;
   std::vector<Sc> res(parts);
-  std::vector<std::thread> th;
-  for (size_t t = 0; t < parts; ++t)
-    th.emplace_back([&, t]() {
-      size_t s = t * chunk, e = std::min(n, s + chunk);
-      Sc acc = Sc::zero(); for (size_t i = e; i-- > s;) acc = acc * x + c[i];
-      res[t] = acc * x.pow_u64(s);
-    });
-  for (auto& t : th) t.join();
+  Pool::get().run(parts, [&](size_t t) {
+    size_t s = t * chunk, e = std::min(n, s + chunk);
+    Sc acc = Sc::zero(); for (size_t i = e; i-- > s;) acc = acc * x + c[i];
+    res[t] = acc * x.pow_u64(s);
+  });
   Sc acc = Sc::zero(); for (auto& r : res) acc = acc + r;
   return acc;
 }
