@@ -102,9 +102,27 @@ class CpuFarm:
     THREADS = 4
     GB_PER_WORKER = 3.0   # resident set is about 1.2 GB per prover (keys + one proof in flight); headroom for the extended-domain buffers
 
+    @staticmethod
+    def host_threads():
+        """hardware threads this process may really use: the affinity mask, cut by a cgroup CPU quota when the container has one"""
+        hw = len(os.sched_getaffinity(0))
+        try:
+            quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]   # cgroup v2
+            if quota != "max":
+                hw = min(hw, max(1, int(float(quota) / float(period))))
+        except (OSError, ValueError):
+            try:   # cgroup v1
+                q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+                p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    hw = min(hw, max(1, q // p))
+            except (OSError, ValueError):
+                pass
+        return hw
+
     def __init__(self, workers=None, threads=None):
         import subprocess
-        hw = len(os.sched_getaffinity(0))
+        hw = self.host_threads()
         self.threads = threads or int(os.environ.get("TB_CPU_THREADS_PER_PROVER", min(self.THREADS, hw)))
         w = workers or int(os.environ.get("TB_CPU_PROVERS", max(1, hw // self.threads)))
         try:
@@ -120,23 +138,24 @@ class CpuFarm:
             if p.stdout.readline().strip() != "ready":
                 raise RuntimeError("CPU prover worker failed to start")
 
-    def sample(self):
-        """Every worker proves 1 Compliance-shaped + 1 VP-shaped proof at the same time; returns the cpu_baseline object."""
+    def sample(self, provers=None):
+        """Every worker (or the first `provers` of them) proves 1 Compliance-shaped + 1 VP-shaped proof at the same time; returns the cpu_baseline object."""
+        procs = self.procs[:provers] if provers else self.procs
         t = time.time()
-        for p in self.procs:
+        for p in procs:
             p.stdin.write("go\n")
             p.stdin.flush()
-        res = [tuple(float(x) for x in p.stdout.readline().split()) for p in self.procs]
+        res = [tuple(float(x) for x in p.stdout.readline().split()) for p in procs]
         wall = time.time() - t
         if any(len(r) != 2 for r in res):
             raise RuntimeError("CPU prover worker died")
         val = sum(1.0 / (2 * c + 4 * v) for c, v in res)   # each prover's serial-loop rate (2C + 4V per ptx, shielded_ptx.rs:107-125), summed
         cs, vs = sorted(c for c, _ in res), sorted(v for _, v in res)
         pub = 2 * PUBLISHED["compliance_proof_s"] + 4 * PUBLISHED["vp_proof_s"]
-        return {"value": val, "unit": "ptx/s", "cores": self.workers * self.threads, "kind": "port",
+        return {"value": val, "unit": "ptx/s", "cores": len(procs) * self.threads, "kind": "port",
                 "sample": "%d concurrent prover processes x %d threads, each proving 1 Compliance-shaped + 1 VP-shaped proof (k=15) in %.1f s of wall time; "
-                          "value = sum over provers of 1/(2C+4V) seconds per ptx" % (self.workers, self.threads, wall),
-                "provers": self.workers, "threads_per_prover": self.threads, "sample_wall_s": round(wall, 2),
+                          "value = sum over provers of 1/(2C+4V) seconds per ptx" % (len(procs), self.threads, wall),
+                "provers": len(procs), "threads_per_prover": self.threads, "sample_wall_s": round(wall, 2),
                 "compliance_proof_s": round(cs[len(cs) // 2], 3), "vp_proof_s": round(vs[len(vs) // 2], 3),
                 "reference_published": dict(PUBLISHED, ptx_per_s=round(1.0 / pub, 5))}
 
@@ -345,7 +364,7 @@ def main():
 
     from taiga_b200 import ptx, shard
     # witness-synthesis workers, forked before CUDA / threads exist; the host cores are shared by the ranks of a multi-GPU run
-    spool = ptx.SynthPool(int(os.environ.get("TB_SYNTH_PROCS", 0)) or min(64, max(4, ((os.cpu_count() or 8) - 2) // max(1, world))))
+    spool = ptx.SynthPool(int(os.environ.get("TB_SYNTH_PROCS", 0)) or min(64, max(4, (CpuFarm.host_threads() - 2) // max(1, world))))
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
@@ -423,8 +442,6 @@ def main():
     # previous batch is proved; every step's advice comes from pageable shared memory through the C ABI (H2D inside the timed region)
     synth_pipe = None
     if not args.no_synth_pipeline and P > 1:
-        nxt = {}
-
         rt = torch.cuda.cudart()
         locked = set()
 
@@ -443,38 +460,74 @@ def main():
                 locked.discard(a.ctypes.data)
                 rt.cudaHostUnregister(a.ctypes.data)
 
-        def synth(i):
-            w_ = svc.synthesize_ptx(P, wseed=1000 + 10 * rank + i, pool=spool)
-            for key in ("c_adv", "v_adv"):   # page-lock the shared memory in the background so that the upload is one fast DMA
-                page_lock(w_[key], True)
-            nxt[i] = w_
-        th = threading.Thread(target=synth, args=(0,))
-        th.start()
-        th.join()
+        # three stages, each on its own thread, one step apart: synthesis (forked processes) -> page-locking -> proving (+ release)
+        import queue
         psteps = 3
+        q_synth, q_ready, q_done = queue.Queue(maxsize=1), queue.Queue(maxsize=1), queue.Queue()
+        stage_s = {"synthesis": 0.0, "page_lock": 0.0, "prove": 0.0, "release": 0.0}
+
+        import shutil
+        set_bytes = wit["c_adv"].nbytes + wit["v_adv"].nbytes
+        live = threading.Semaphore(3 if shutil.disk_usage("/dev/shm").free > 3.3 * set_bytes else 2)   # witness sets alive at once (4 GB each at P = 64)
+
+        def stage_synth():
+            for i in range(psteps + 1):
+                live.acquire()
+                t_ = time.time()
+                w_ = svc.synthesize_ptx(P, wseed=1000 + 10 * rank + i, pool=spool)
+                stage_s["synthesis"] += time.time() - t_
+                q_synth.put(w_)
+
+        def stage_lock():
+            for i in range(psteps + 1):
+                w_ = q_synth.get()
+                t_ = time.time()
+                for key in ("c_adv", "v_adv"):   # page-lock the shared memory so that the upload is one fast DMA
+                    page_lock(w_[key], True)
+                stage_s["page_lock"] += time.time() - t_
+                q_ready.put(w_)
+
+        def stage_release():
+            while True:
+                w_ = q_done.get()
+                if w_ is None:
+                    return
+                t_ = time.time()
+                for key in ("c_adv", "v_adv"):
+                    page_lock(w_[key], False)
+                stage_s["release"] += time.time() - t_
+                del w_
+                live.release()
+
+        ths = [threading.Thread(target=f) for f in (stage_synth, stage_lock, stage_release)]
+        for th in ths:
+            th.start()
+        cur = q_ready.get()   # the first step's witnesses are ready before the clock starts (steady state of a service)
+        page_locked_any = len(locked) > 0
+        for key in stage_s:
+            stage_s[key] = 0.0
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.time()
-        page_locked_any = len(locked) > 0
         for i in range(psteps):
-            cur = nxt.pop(i)
-            th = threading.Thread(target=synth, args=(i + 1,))
-            th.start()
+            t_ = time.time()
             step(200 + i, False, w=cur, cd=cur["c_adv"], vd=cur["v_adv"])
-            for key in ("c_adv", "v_adv"):
-                page_lock(cur[key], False)
-            th.join()
+            stage_s["prove"] += time.time() - t_
+            q_done.put(cur)
+            cur = q_ready.get()   # the witnesses of the next step (the last one is synthesised but not proved: steady state)
         torch.cuda.synchronize()
         pw = torch.tensor([(time.time() - t0) * 1e3], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(pw, op=dist.ReduceOp.MAX)
-        for w_ in nxt.values():
-            for key in ("c_adv", "v_adv"):
-                page_lock(w_[key], False)
-        nxt.clear()
+        q_done.put(cur)
+        q_done.put(None)
+        for th in ths:
+            th.join()
         synth_pipe = {"page_locked": bool(page_locked_any), "value": round(P * world / (float(pw[0]) * 1e-3 / psteps), 4), "unit": "ptx/s", "steps": psteps,
-                      "note": "fresh witnesses every step, synthesised by forked host processes while the previous step is proved; advice page-locked in the background (cudaHostRegister) and uploaded through the C ABI"}
+                      "stage_seconds_per_step": {k_: round(v_ / psteps, 3) for k_, v_ in stage_s.items()},
+                      "note": "fresh witnesses every step; three host stages one step apart: synthesis by forked host processes, page-locking (cudaHostRegister) of the shared-memory advice, "
+                              "proving through the C ABI; the slowest stage sets the rate"}
 
     # one profiled step (CUDA events around every kernel group) for the share-of-step table and the roofline.  It runs the
     # workers one after the other: with the streams overlapped an event pair also times the wait for SMs held by the other
