@@ -363,8 +363,10 @@ def main():
         return
 
     from taiga_b200 import ptx, shard
-    # witness-synthesis workers, forked before CUDA / threads exist; the host cores are shared by the ranks of a multi-GPU run
-    spool = ptx.SynthPool(int(os.environ.get("TB_SYNTH_PROCS", 0)) or min(64, max(4, (CpuFarm.host_threads() - 2) // max(1, world))))
+    # witness-synthesis workers, forked before CUDA / threads exist; the host cores are shared by the ranks of a multi-GPU run.
+    # Half of the usable hardware threads: with more, the overlapped pipeline starves the proving threads (16-CPU quota on the
+    # B200 box: 14 processes -> 18.0 ptx/s overlapped, 11 -> 18.8, 8 -> 19.9; profiles/r02_bench_synth_pipe_procs8.json)
+    spool = ptx.SynthPool(int(os.environ.get("TB_SYNTH_PROCS", 0)) or min(64, max(4, (CpuFarm.host_threads() // 2) // max(1, world))))
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
