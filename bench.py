@@ -355,12 +355,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-synth-pipeline", action="store_true")
+    ap.add_argument("--all-probes", action="store_true", help="multi-GPU runs skip the secondary probes (single-ptx latency, overlapped synthesis) unless this is given")
     ap.add_argument("--serial", action="store_true", help="one stream, no threads (for ncu launch lists; not a benchmark configuration)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if world > 1 and not args.all_probes:   # the scaling runs need value / e2e; the secondary probes cost host cores and minutes on every rank
+        args.no_latency = args.no_synth_pipeline = True
 
     from taiga_b200 import ptx, shard
     # witness-synthesis workers, forked before CUDA / threads exist; the host cores are shared by the ranks of a multi-GPU run.
@@ -642,7 +645,7 @@ def main():
         pass
     if not args.no_sweep and world == 1:
         line["sweeps"] = sweep(ctx, hbm_peak, quick=not args.full_sweep)
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # the CPU arm is timed on rank 0 of a single-GPU run only
         farm = CpuFarm()
         try:
             line["cpu_baseline"] = farm.sample()
