@@ -23,30 +23,32 @@ inline int& num_threads() { static int n = std::max(1u, std::thread::hardware_co
 class Pool {
  public:
   static Pool& get() { static Pool p; return p; }
-  // runs task(0) .. task(count - 1) on up to `count` threads (the caller takes part); returns when all are done
+  // runs task(0) .. task(count - 1) on up to min(count, num_threads()) threads (the caller takes part); returns when all are done.
+  // Only as many workers as the job can use are woken: on a 128-thread host a 4-thread prover must not wake 127 sleepers per FFT stage.
   void run(size_t count, const std::function<void(size_t)>& task) {
     if (count == 0) return;
-    if (count == 1 || in_task() || workers_.empty()) { for (size_t i = 0; i < count; ++i) task(i); return; }
+    const size_t want = std::min(count - 1, (size_t)std::max(0, num_threads() - 1));
+    if (want == 0 || in_task()) { for (size_t i = 0; i < count; ++i) task(i); return; }
     std::unique_lock<std::mutex> job_lock(job_mu_);   // one job at a time
+    size_t have;
     { std::lock_guard<std::mutex> lk(mu_);
-      task_ = &task; count_ = count; next_.store(0); pending_.store(count); ++epoch_; }
-    cv_.notify_all();
+      while (workers_.size() < want) workers_.emplace_back([this] { loop(); });   // workers are created on demand, never more than a job asked for
+      have = workers_.size();
+      task_ = &task; count_ = count; next_.store(0); pending_.store(count); tickets_ = want; }
+    if (want >= have) cv_.notify_all(); else for (size_t i = 0; i < want; ++i) cv_.notify_one();
     work();
     std::unique_lock<std::mutex> lk(mu_);
     done_cv_.wait(lk, [&] { return pending_.load() == 0 && active_ == 0; });   // nobody is still polling this job's counter
-    task_ = nullptr;
+    tickets_ = 0; task_ = nullptr;
   }
   ~Pool() {
-    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; ++epoch_; }
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
     cv_.notify_all();
     for (auto& t : workers_) t.join();
   }
 
  private:
-  Pool() {
-    unsigned n = std::max(1u, std::thread::hardware_concurrency());
-    for (unsigned i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
-  }
+  Pool() {}
   static bool& in_task() { static thread_local bool f = false; return f; }
   void work() {
     in_task() = true;
@@ -59,14 +61,11 @@ class Pool {
     in_task() = false;
   }
   void loop() {
-    uint64_t seen = 0;
     for (;;) {
       { std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return epoch_ != seen; });
-        seen = epoch_;
+        cv_.wait(lk, [&] { return stop_ || tickets_ > 0; });
         if (stop_) return;
-        if (!task_) continue;
-        ++active_; }
+        --tickets_; ++active_; }
       work();
       { std::lock_guard<std::mutex> lk(mu_); --active_; }
       done_cv_.notify_all();
@@ -76,9 +75,8 @@ class Pool {
   std::mutex mu_, job_mu_;
   std::condition_variable cv_, done_cv_;
   const std::function<void(size_t)>* task_ = nullptr;
-  size_t count_ = 0;
+  size_t count_ = 0, tickets_ = 0;   // tickets_: workers still invited to the current job (guarded by mu_)
   std::atomic<size_t> next_{0}, pending_{0};
-  uint64_t epoch_ = 0;
   int active_ = 0;   // workers inside work() (guarded by mu_)
   bool stop_ = false;
 };
