@@ -8,7 +8,11 @@
 //
 // Blinding randomness: the reference draws from the caller's RNG; here every random scalar is derived from a
 // 32-byte seed with a BLAKE2b PRF (rnd()) so that the CUDA prover can be compared byte for byte.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
+#include <string>
 #include <set>
 #include "../include/taiga_b200.h"
 #include "blake2b.hpp"
@@ -105,6 +109,26 @@ struct Transcript {
   }
 };
 
+// optional phase timers (ORC_TIMING=1): where a CPU proof spends its time; test infrastructure only
+struct PhaseTimer {
+  static std::map<std::string, double>& table() { static std::map<std::string, double> t; return t; }
+  static bool on() { static bool f = getenv("ORC_TIMING") != nullptr; return f; }
+  const char* name; std::chrono::steady_clock::time_point t0;
+  explicit PhaseTimer(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {}
+  ~PhaseTimer() { if (on()) table()[name] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+  static void report() {
+    if (!on()) return;
+    double tot = 0; for (auto& kv : table()) tot += kv.second;
+    for (auto& kv : table()) fprintf(stderr, "[orc] %-22s %8.3f s %5.1f %%\n", kv.first.c_str(), kv.second, 100 * kv.second / tot);
+    table().clear();
+  }
+};
+struct PhaseSeq {   // consecutive phases of prove(): next("x") closes the previous one
+  PhaseTimer* cur = nullptr;
+  void next(const char* n) { delete cur; cur = n ? new PhaseTimer(n) : nullptr; }
+  ~PhaseSeq() { delete cur; }
+};
+
 struct Key {
   Desc d; Domain<Fp> dom; size_t n; int chunk_len; size_t nsets;
   std::vector<Pt> g, gl; Pt w, u;
@@ -114,6 +138,7 @@ struct Key {
   Key(const tb_cs_desc* c) : d(c), dom(c->cs_degree, c->k), n(size_t(1) << c->k) {}
 
   JPt commit(const std::vector<Pt>& bases, const std::vector<Fp>& v, const Fp& blind) const {
+    PhaseTimer pt("commit (n-term MSM)");
     JPt r = msm<Fq, Fp>(v.data(), bases.data(), v.size());
     u64 b[4]; blind.to_canonical(b);
     return r.add(JPt::from_affine(w).mul(b));
@@ -251,6 +276,8 @@ static int prove(const Key& key, const uint8_t* advice_bytes, const uint8_t* ins
   int ext_shift = dom.ext_k - dom.k; size_t rot_scale = size_t(1) << ext_shift;
   Transcript tr;
   tr.common_scalar(d.vk_repr);
+  PhaseSeq ph;
+  ph.next("1 instance+advice (incl. commits, ffts)");
   // ---- instance columns
   std::vector<std::vector<Fp>> inst_vals(d.ni), inst_polys(d.ni), inst_cosets(d.ni);
   { size_t off = 0;
@@ -274,6 +301,7 @@ static int prove(const Key& key, const uint8_t* advice_bytes, const uint8_t* ins
   for (uint32_t c = 0; c < d.na; ++c) tr.write_point(key.commit(key.gl, adv_vals[c], adv_blinds[c]).to_affine());
   for (uint32_t c = 0; c < d.na; ++c) { adv_polys[c] = adv_vals[c]; dom.lagrange_to_coeff(adv_polys[c]); adv_cosets[c] = dom.coeff_to_extended(adv_polys[c]); }
   Fp theta = tr.squeeze();
+  ph.next("2 lookups permute (incl.)");
   // ---- lookups: compress, permute, commit A', S'
   size_t nl = d.lookups.size();
   std::vector<std::vector<Fp>> lk_in(nl), lk_tab(nl), lk_pin(nl), lk_ptab(nl), lk_pin_poly(nl), lk_ptab_poly(nl), lk_pin_coset(nl), lk_ptab_coset(nl);
@@ -302,6 +330,7 @@ static int prove(const Key& key, const uint8_t* advice_bytes, const uint8_t* ins
     lk_ptab_poly[l] = lk_ptab[l]; dom.lagrange_to_coeff(lk_ptab_poly[l]); lk_ptab_coset[l] = dom.coeff_to_extended(lk_ptab_poly[l]);
   }
   Fp beta = tr.squeeze(), gamma = tr.squeeze();
+  ph.next("3 perm products (incl.)");
   // ---- permutation argument: grand products
   auto col_vals = [&](const tb_column& c) -> const std::vector<Fp>& {
     return c.kind == TB_COL_ADVICE ? adv_vals[c.index] : c.kind == TB_COL_FIXED ? key.fixed_vals[c.index] : inst_vals[c.index]; };
@@ -328,6 +357,7 @@ static int prove(const Key& key, const uint8_t* advice_bytes, const uint8_t* ins
       tr.write_point(key.commit(key.gl, z, pz_blind[s]).to_affine());
       dom.lagrange_to_coeff(z); pz_poly[s] = z; pz_coset[s] = dom.coeff_to_extended(z);
     } }
+  ph.next("4 lookup products (incl.)");
   // ---- lookup grand products
   std::vector<std::vector<Fp>> lz_poly(nl), lz_coset(nl); std::vector<Fp> lz_blind(nl);
   for (size_t l = 0; l < nl; ++l) {
@@ -342,12 +372,14 @@ static int prove(const Key& key, const uint8_t* advice_bytes, const uint8_t* ins
     tr.write_point(key.commit(key.gl, z, lz_blind[l]).to_affine());
     dom.lagrange_to_coeff(z); lz_poly[l] = z; lz_coset[l] = dom.coeff_to_extended(z);
   }
+  ph.next("5 random poly (incl.)");
   // ---- vanishing argument: random polynomial
   std::vector<Fp> random_poly(n);
   for (size_t i = 0; i < n; ++i) random_poly[i] = rnd(seed, pidx, R_RANDOM_POLY, (uint32_t)i);
   Fp random_blind = rnd(seed, pidx, R_RANDOM_BLIND, 0);
   tr.write_point(key.commit(key.g, random_poly, random_blind).to_affine());
   Fp y = tr.squeeze();
+  ph.next("6 quotient eval");
   // ---- quotient h(X) on the extended domain
   std::vector<Fp> h(ext_n);
   { Fp delta = Fp::delta(); int last_rot = -(int)(bf + 1);
@@ -394,6 +426,7 @@ static int prove(const Key& key, const uint8_t* advice_bytes, const uint8_t* ins
         h[i] = acc;
       }
     }); }
+  ph.next("7 h to coeff + commit (incl.)");
   dom.divide_by_vanishing_poly(h);
   std::vector<Fp> hc = dom.extended_to_coeff(h);
   size_t npieces = dom.quotient_poly_degree;
@@ -402,6 +435,7 @@ static int prove(const Key& key, const uint8_t* advice_bytes, const uint8_t* ins
   for (size_t p = 0; p < npieces; ++p) tr.write_point(key.commit(key.g, h_pieces[p], h_blinds[p]).to_affine());
   Fp x = tr.squeeze();
   Fp xn = x.pow_u64(n);
+  ph.next("8 evaluations");
   // ---- evaluations
   auto ev = [&](const std::vector<Fp>& poly, int rot) { return eval_polynomial(poly.data(), poly.size(), dom.rotate_omega(x, rot)); };
   for (auto& q : d.iq) tr.write_scalar(ev(inst_polys[q.column], q.rotation));
@@ -434,6 +468,7 @@ static int prove(const Key& key, const uint8_t* advice_bytes, const uint8_t* ins
   for (size_t c = 0; c < P; ++c) qs.push_back({&key.sig_polys[c], one, 0});
   qs.push_back({&h_poly, h_blind, 0});
   qs.push_back({&random_poly, random_blind, 0});
+  ph.next("9 multiopen (incl.)");
   // ---- multiopen::create_proof
   Fp x1 = tr.squeeze(), x2 = tr.squeeze();
   std::vector<const void*> ids; for (auto& q : qs) ids.push_back(q.poly);
@@ -460,7 +495,10 @@ static int prove(const Key& key, const uint8_t* advice_bytes, const uint8_t* ins
   Fp x4 = tr.squeeze();
   std::vector<Fp> p_poly = q_prime; Fp p_blind = q_prime_blind;
   for (size_t si = 0; si < ns; ++si) { for (size_t i = 0; i < n; ++i) p_poly[i] = p_poly[i] * x4 + q_polys[si][i]; p_blind = p_blind * x4 + q_blinds[si]; }
+  ph.next("A ipa (incl.)");
   ipa_prove(key, tr, seed, pidx, p_poly, p_blind, x3);
+  ph.next(nullptr);
+  PhaseTimer::report();
   if (tr.bad) return 4;
   out = tr.proof;
   return 0;
