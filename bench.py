@@ -136,6 +136,8 @@ class CpuFarm:
                                        text=True, env=env) for _ in range(w)]
         for p in self.procs:
             if p.stdout.readline().strip() != "ready":
+                for q in self.procs:
+                    q.kill()
                 raise RuntimeError("CPU prover worker failed to start")
 
     def sample(self, provers=None):
@@ -646,13 +648,16 @@ def main():
     if not args.no_sweep and world == 1:
         line["sweeps"] = sweep(ctx, hbm_peak, quick=not args.full_sweep)
     if not args.no_cpu and world == 1:   # the CPU arm is timed on rank 0 of a single-GPU run only
-        farm = CpuFarm()
-        try:
-            line["cpu_baseline"] = farm.sample()
-        finally:
-            farm.close()
-        line["speedup_e2e_vs_cpu_port"] = round(e2e_val / line["cpu_baseline"]["value"], 2)
-        line["speedup_e2e_vs_published_reference"] = round(e2e_val / line["cpu_baseline"]["reference_published"]["ptx_per_s"], 2)
+        try:   # a failure of the CPU arm must not cost the GPU line
+            farm = CpuFarm()
+            try:
+                line["cpu_baseline"] = farm.sample()
+            finally:
+                farm.close()
+            line["speedup_e2e_vs_cpu_port"] = round(e2e_val / line["cpu_baseline"]["value"], 2)
+            line["speedup_e2e_vs_published_reference"] = round(e2e_val / line["cpu_baseline"]["reference_published"]["ptx_per_s"], 2)
+        except Exception as ex:  # pragma: no cover
+            line["cpu_baseline"] = {"value": None, "unit": "ptx/s", "kind": "port", "error": repr(ex)}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
